@@ -1,0 +1,59 @@
+"""oracle/beam.py is UNPINNED against pyctcdecode (unavailable); these tests freeze the restatement
+(tests/golden/beam_restatement.npz) and check properties any faithful prefix beam search has."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import beam as ob
+from oracle import greedy as og
+from silent_speech_decoder_b200 import synth
+from silent_speech_decoder_b200.data.vocab import Vocab
+
+NAMES = ["peaked50", "flat50", "flat20_bias", "peaked100_p12", "flat1", "flat200"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_frozen_outputs(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "beam_restatement.npz"))
+    v = Vocab.default()
+    width, prune, bias = z[f"{name}.cfg"]
+    dec = ob.BeamDecoder(v.tokens, v.blank_id, v.pad_id, int(width), float(prune), float(bias))
+    out = dec.decode_with_scores(z[f"{name}.lp"], z[f"{name}.len"])
+    assert [t for t, _ in out] == list(z[f"{name}.text"])
+    np.testing.assert_allclose([s for _, s in out], z[f"{name}.score"], rtol=0, atol=1e-9)
+
+
+def test_labels_follow_reference_wrapper():
+    v = Vocab.default()
+    keep, raw = ob.beam_labels(v.tokens, v.blank_id, v.pad_id)
+    assert keep == list(range(2, 48)) and raw[0] == "" and len(raw) == 47
+    lab = ob.normalize_labels(raw)
+    assert lab[1] == ob.UNK_GLYPH and lab[2] == " " and lab[0] == ""
+
+
+def test_pad_mass_is_folded_into_blank():
+    v = Vocab.default()
+    lp = synth.flat(1, 3, 5).numpy()
+    m = ob.wrapper_matrix(lp, v.blank_id, v.pad_id, 0.0, list(range(2, 48)))
+    np.testing.assert_allclose(np.exp(m).sum(-1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(m[0, :, 0], np.logaddexp(lp[0, :, 1], lp[0, :, 0]), atol=1e-6)
+
+
+def test_width1_on_peaked_equals_greedy_text():
+    # with sharply peaked posteriors the single best beam is the collapsed argmax path
+    v = Vocab.default()
+    lp = synth.peaked(3, 80, 11, boost=14.0).numpy()
+    ln = [80, 80, 40]
+    dec = ob.BeamDecoder(v.tokens, v.blank_id, v.pad_id, beam_width=1)
+    g = og.greedy_text(lp, ln, v.tokens, v.blank_id, v.pad_id)
+    assert dec(lp, ln) == [" ".join(s.split()) for s in g]
+
+
+def test_empty_and_unk():
+    v = Vocab.default()
+    dec = ob.BeamDecoder(v.tokens, v.blank_id, v.pad_id)
+    lp = np.full((1, 4, 48), -20.0, dtype=np.float32)
+    lp[0, :, v.unk_id] = 0.0
+    assert dec(lp, [0]) == [""]
+    assert dec(lp, [4]) == [ob.UNK_GLYPH]
