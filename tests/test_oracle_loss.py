@@ -35,8 +35,8 @@ def test_numpy_restatement_matches_reference(golden_dir, name):
     np.testing.assert_allclose(grad, c["grad64"], rtol=0, atol=1e-13)
     # vs the reference module (fp32): its own rounding is the limit
     assert abs(mean - float(c["ref_ctc"])) <= 2e-6 * max(1.0, abs(mean))
-    # (already ~1e-5 normwise at T=40: fp32 log-space rounding inside ATen)
-    assert np.abs(grad - c["ref_grad"]).max() <= 1e-4 * max(np.abs(grad).max(), 1e-30) + 1e-8
+    # (already 1e-5..1e-4 normwise at T=40..60: fp32 log-space rounding inside ATen)
+    assert np.abs(grad - c["ref_grad"]).max() <= 1e-3 * max(np.abs(grad).max(), 1e-30) + 1e-8
 
 
 def test_edge_semantics(golden_dir):
