@@ -1,0 +1,113 @@
+/* ssd_ctc.h -- C ABI of the B200-native CTC hot path (libssd_ctc.so, sm_100a).
+ *
+ * The reference (ajshul/silent-speech-decoder) is pure Python and has no FFI; the two call
+ * sites this library stands behind are
+ *
+ *   src/models/losses.py:56    self.ctc_loss(log_probs_t, targets, ctc_lengths, target_lengths)
+ *                              (nn.CTCLoss(blank=blank_id, zero_infinity=True), :28)  -> ssd_ctc_loss
+ *   src/decoding/ctc.py:21-35  torch.argmax + collapse loop (_greedy_decode)           -> ssd_ctc_greedy
+ *   src/decoding/ctc.py:75-96  pad->blank merge, label permutation, per-utterance
+ *                              pyctcdecode decoder.decode(lp, beam_width, beam_prune_logp) -> ssd_ctc_beam
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers (HBM).  The library never allocates, frees or
+ *     retains device memory: the caller owns every buffer, including the workspace.
+ *   - log_probs is fp32 with element strides (stride_b, stride_t, 1): element (b,t,v) lives at
+ *     log_probs[b*stride_b + t*stride_t + v].  The reference's tensors are (B,T,V) contiguous
+ *     (heads.py:37) viewed as (T,B,V) (losses.py:53): stride_b = T*V, stride_t = V.
+ *   - lengths / ids are int64, as the reference's collate function produces them
+ *     (src/data/dataset.py:143,206).
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and the call returns without synchronising.
+ *   - Every function returns SSD_OK or an error code; ssd_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws or aborts across this boundary and
+ *     there is no CPU fallback.
+ */
+#ifndef SSD_CTC_H_
+#define SSD_CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_ABI_VERSION 1
+
+enum {
+  SSD_OK = 0,
+  SSD_ERR_BAD_ARG = 1,     /* null pointer, negative size, bad stride, id out of range */
+  SSD_ERR_UNSUPPORTED = 2, /* shape outside what the kernels are built for */
+  SSD_ERR_WORKSPACE = 3,   /* workspace missing or too small */
+  SSD_ERR_CUDA = 4         /* a CUDA runtime call or launch failed */
+};
+
+/* Limits of this build. */
+#define SSD_MAX_VOCAB 128      /* V */
+#define SSD_MAX_TARGET 511     /* S: extended length 2S+1 <= 1023 lanes of the alpha/beta recursion */
+#define SSD_MAX_BEAM 512       /* beam_width */
+
+int ssd_abi_version(void);
+const char* ssd_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Greedy decode: per frame argmax over V (first maximum wins, like torch.argmax on CPU), then
+ * collapse: a frame emits its label iff it is not `blank` and differs from the previous frame's
+ * argmax (src/decoding/ctc.py:23-35).  blank_bias is added to column `blank` in fp32 before
+ * the argmax (ctc.py:18-20).
+ *   lengths      [B] frames per utterance, clamped to [0,T]
+ *   out_tokens   [B,T] int32, row b holds out_lengths[b] vocabulary ids
+ *   out_lengths  [B]   int32
+ */
+int ssd_ctc_greedy(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                   const int64_t* lengths, int blank, float blank_bias, int32_t* out_tokens, int32_t* out_lengths,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Prefix beam search with pyctcdecode's no-LM semantics, as invoked by src/decoding/ctc.py:89-96.
+ * Done in-kernel per frame: blank column = logaddexp(lp[blank]+blank_bias, lp[pad]) (ctc.py:76-81),
+ * the remaining ids in vocabulary order (ctc.py:64-65,84-87), fp32 log-softmax + clip to
+ * [ln 1e-15, 0], candidate filter (>= token_min_logp or argmax), fp64 prefix scores, merge by
+ * (text, last char), relative prune, top beam_width, history prune on (last word, open word,
+ * last char), final merge of blank-/char-ending variants.
+ *   pad          vocabulary id folded into blank, or -1
+ *   space        vocabulary id of the word separator " ", or -1
+ *   order        [B] int32 processing order (e.g. longest first), or NULL for 0..B-1
+ *   out_tokens   [B,T] int32 vocabulary ids of the best transcript (whitespace-normalised)
+ *   out_lengths  [B]   int32
+ *   out_scores   [B]   fp64 log-score of the best transcript, or NULL
+ */
+size_t ssd_ctc_beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int beam_width);
+int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                 const int64_t* lengths, const int32_t* order, int blank, int pad, int space, float blank_bias,
+                 int beam_width, float beam_prune_logp, float token_min_logp, int32_t* out_tokens,
+                 int32_t* out_lengths, double* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CTC loss, forward and backward in one launch (torch.nn.CTCLoss semantics, reduction 'none'
+ * for the returned values; the gradient can be pre-scaled for reduction 'mean').
+ *   targets        [B, >=S_max] int64 padded label matrix with row stride tgt_stride (elements)
+ *   input_lengths  [B] frames  (<= T)        target_lengths [B] labels (<= S_max)
+ *   order          [B] int32 processing order or NULL
+ *   nll            [B] fp32: -log p(target | input); +inf if infeasible, 0 if zero_infinity
+ *   grad           same layout and strides as log_probs, or NULL for forward only.
+ *                  grad[b,t,:] = scale_b * (exp(lp) - posterior), 0 for t >= input_lengths[b] and
+ *                  for infeasible rows (zero_infinity).  scale_b = 1 if mean_denominator == 0,
+ *                  else 1 / (mean_denominator * max(target_lengths[b],1))  -- pass the GLOBAL
+ *                  batch size to obtain d(mean loss)/d(log_probs) without any exchange of
+ *                  gradients between data-parallel ranks.
+ *   grad_mul       device pointer to one fp32 multiplied into the gradient (autograd's incoming
+ *                  grad_output), or NULL for 1
+ */
+size_t ssd_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                 const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
+                 const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
+                 int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD_CTC_H_ */

@@ -1,0 +1,816 @@
+// CTC prefix beam search, one CTA per utterance, pyctcdecode (no-LM) semantics.
+//
+// Replaces reference src/decoding/ctc.py:74-97 (wrapper) + pyctcdecode.BeamSearchDecoderCTC.decode
+// (third-party, restated in oracle/beam.py).  See DESIGN.md section 5 for the derivation.
+//
+// State.  pyctcdecode keys a beam by (text, open word, last char).  For a fixed text the last
+// char is either "" (blank) or the last emitted character, so the beam is held as PREFIXES, each
+// with two fp64 scores: sb (ends in blank) and snb (ends in its last character) -- but, as
+// upstream does, each of the two is ranked, pruned and history-pruned as a separate entry.
+// A prefix carries 64-bit rolling hashes of its text (merge key), of its parent's text, of its
+// text without a trailing space (final merge), of its last closed word and of its open word
+// (history key), its last label, its length and a back-pointer node for the transcript.
+// Space handling follows upstream's whitespace-safe merge: a space after "" or after a closed
+// word is absorbed (it only changes the last char), so "a" + " " + " " and "a" + " " are one text.
+//
+// Per frame (4 consumer warps; warp 4 conditions the next frame's row concurrently):
+//   1  tot = logaddexp(sb, snb); locate parent prefix through the shared-memory hash table
+//   2  rank prefixes by tot; blank / repeat / parent-extension scores of every live prefix
+//   3  proposals P+c.  With prefixes ranked by tot and candidate labels by log-prob, proposal
+//      (i,j) is dominated by (i+1)*j others, so only j <= W/(i+1) can reach the top W: about
+//      W(ln W + 1.6) proposals instead of W*46.  Proposals whose text is already a live prefix are
+//      folded into that prefix's snb (step 2) and dropped here.
+//   4  block max, relative prune, exact top-W by rank counting (ties: lower candidate index)
+//   5  history prune: best entry per (last closed word, open word, last char)
+//   6  compact survivors into the next prefix table, append back-pointer nodes, rebuild hash table
+// End: merge blank-/char-ending and trailing-space variants, arg-max, walk back-pointers.
+#include <cmath>
+
+#include "ssd_common.cuh"
+
+namespace ssd {
+
+constexpr int BM_CONS = 128;             // consumer threads (warps 0-3)
+constexpr int BM_THREADS = BM_CONS + 32;  // + producer warp
+constexpr int BM_CHUNK = 16;             // frames per TMA chunk
+constexpr int BAR_CONS = 1;              // named barrier: consumers only
+constexpr int BAR_FRAME = 2;             // named barrier: consumers + producer, once per frame
+constexpr int LBL_NONE = 255;
+
+struct BeamParams {
+  const float* lp;
+  int64_t T, sb, st;
+  int B, V;
+  const int64_t* lengths;
+  const int32_t* order;
+  int blank, pad, space;
+  float bias, prune, tmin;
+  int W;
+  int32_t* out_tok;
+  int32_t* out_len;
+  double* out_score;
+  unsigned* counter;     // work queue head
+  uint2* nodes;          // [grid][node_cap] back-pointers
+  int64_t node_cap;
+  int use_tma;
+  // derived sizes
+  int VL;     // labels after dropping blank/pad: 1 + #others
+  int TS;     // hash table slots (pow2)
+  int NCAND;  // candidate capacity
+};
+
+__host__ __device__ inline int beam_ncand_cap(int W, int VL) {
+  // 2 entries per live prefix + staircase sum_{i<W} min(VL-1, W/(i+1)+1)
+  long n = 2L * W;
+  for (int i = 0; i < W; ++i) {
+    int j = W / (i + 1) + 1;
+    n += j < VL - 1 ? j : VL - 1;
+  }
+  return (int)((n + 31) / 32 * 32);
+}
+__host__ __device__ inline int beam_table_slots(int W) {
+  int ts = 64;
+  while (ts < 4 * W) ts <<= 1;
+  return ts;
+}
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ uint64_t hmix(uint64_t h, uint32_t c) {
+  uint64_t x = h ^ (0x9E3779B97F4A7C15ull * (uint64_t)(c + 1u));
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  return x ? x : 1ull;
+}
+__device__ __forceinline__ double neg_inf() { return -INFINITY; }
+// fp64 logaddexp in upstream's form: hi + log(1 + exp(lo - hi))
+__device__ __forceinline__ double lse2(double a, double b) {
+  const double hi = a >= b ? a : b, lo = a >= b ? b : a;
+  if (lo == -INFINITY) return hi;
+  return hi + log(1.0 + exp(lo - hi));
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double x = __shfl_xor_sync(FULL, v, o);
+    v = x > v ? x : v;
+  }
+  return v;
+}
+// numpy.logaddexp on fp32
+__device__ __forceinline__ float logaddexp_f32(float x, float y) {
+  if (x == y) return x + 0.69314718055994530942f;
+  const float d = x - y;
+  if (d > 0.f) return x + log1pf(expf(-d));
+  if (d <= 0.f) return y + log1pf(expf(d));
+  return x + y;  // NaN
+}
+
+struct Prefix {  // structure of arrays, two generations
+  uint64_t* H;
+  uint64_t* Hpar;
+  uint64_t* Hstrip;
+  uint64_t* hl;
+  uint64_t* ho;
+  double* sb;
+  double* snb;
+  uint32_t* node;
+  int* last;  // last label (1..VL-1), or LBL_NONE
+  int* len;   // number of labels in the text
+};
+
+__device__ __forceinline__ unsigned char* carve(unsigned char*& p, size_t bytes) {
+  unsigned char* r = p;
+  p += (bytes + 15) & ~(size_t)15;
+  return r;
+}
+__device__ __forceinline__ void carve_prefix(unsigned char*& p, Prefix& a, int W) {
+  a.H = (uint64_t*)carve(p, 8 * W);
+  a.Hpar = (uint64_t*)carve(p, 8 * W);
+  a.Hstrip = (uint64_t*)carve(p, 8 * W);
+  a.hl = (uint64_t*)carve(p, 8 * W);
+  a.ho = (uint64_t*)carve(p, 8 * W);
+  a.sb = (double*)carve(p, 8 * W);
+  a.snb = (double*)carve(p, 8 * W);
+  a.node = (uint32_t*)carve(p, 4 * W);
+  a.last = (int*)carve(p, 4 * W);
+  a.len = (int*)carve(p, 4 * W);
+}
+
+__host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND) {
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  size_t s = 0;
+  s += 2 * (7 * al(8 * (size_t)W) + 3 * al(4 * (size_t)W));  // prefix tables
+  s += 4 * al(8 * (size_t)W);                               // tot, newb, newnb, ext_in
+  s += 6 * al(4 * (size_t)W);                               // par, rnk, rank2p, rowoff, keepflags, slot
+  s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
+  s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // candidate score, desc
+  s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // alive score, alive idx
+  s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
+  s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // sel_hk, sel_lc
+  s += 2 * (al(4 * (size_t)VL) + al(VL));                   // frame records: rl[VL], cs[VL] (x2)
+  s += al(4 * (size_t)VL);                                  // lab2voc
+  s += 2 * al((size_t)BM_CHUNK * V * 4);                    // raw log-prob chunks
+  s += 256;                                                 // scalars, mbarriers
+  return s;
+}
+
+struct FrameRec {
+  float* rl;          // [VL] conditioned log-prob of label k, -inf when not a candidate
+  unsigned char* cs;  // non-blank candidates sorted by log-prob, descending
+};
+
+struct Scal {
+  uint64_t bar[2];
+  double wmax[4];
+  int nc1[2];
+  int np;
+  int n_e3;
+  int n_alive;
+  int n_sel;
+  int n_keep_old;
+  int n_new;
+  int utt;
+  unsigned nodes_used;
+  int wcnt[4];
+};
+
+// ------------------------------------------------------------------ producer: condition one frame
+// All 32 lanes; labels k = lane, lane+32, ...  Mirrors ctc.py:76-87 and decode_beams' fp32
+// log-softmax + clip, then builds the candidate set {k: r_k >= tmin} | {argmax}.
+__device__ void condition_frame(const float* __restrict__ row, const BeamParams& P, const int* __restrict__ lab2voc, FrameRec fr,
+                                int* nc1_out) {
+  const int lane = lane_id();
+  constexpr int PER = SSD_MAX_VOCAB / 32;
+  float x[PER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane + 32 * i;
+    float v = -INFINITY;
+    if (k < P.VL) {
+      if (k == 0) {
+        v = row[P.blank];
+        if (P.bias != 0.f) v = v + P.bias;
+        if (P.pad >= 0 && P.pad != P.blank) v = logaddexp_f32(v, row[P.pad]);
+      } else {
+        v = row[lab2voc[k]];
+      }
+    }
+    x[i] = v;
+    m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if (!(fabsf(m) <= 3.0e38f)) m = 0.f;  // non-finite maximum -> 0, as upstream
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane + 32 * i;
+    x[i] = x[i] - m;
+    if (k < P.VL) s += (double)expf(x[i]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  const float lognorm = logf((float)s);
+  const float lo = -34.538776394910684f;  // fp32(ln 1e-15)
+  float best = -INFINITY;
+  int best_k = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane + 32 * i;
+    float r = x[i] - lognorm;
+    r = fminf(fmaxf(r, lo), 0.f);
+    x[i] = r;
+    if (k < P.VL && (r > best || (r == best && k < best_k))) {
+      best = r;
+      best_k = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(FULL, best, o);
+    const int ok = __shfl_xor_sync(FULL, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane + 32 * i;
+    if (k < P.VL) fr.rl[k] = (x[i] >= P.tmin || k == best_k) ? x[i] : -INFINITY;
+  }
+  __syncwarp();
+  // order non-blank candidates by (log-prob desc, label asc) through rank counting
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int k = lane + 32 * i;
+    if (k >= 1 && k < P.VL && fr.rl[k] != -INFINITY) {
+      const float mine = fr.rl[k];
+      int rank = 0;
+      for (int q = 1; q < P.VL; ++q) {
+        const float o = fr.rl[q];
+        rank += (o > mine || (o == mine && q < k)) ? 1 : 0;  // -inf never outranks a candidate
+      }
+      fr.cs[rank] = (unsigned char)k;
+      ++cnt;
+    }
+  }
+  cnt = __reduce_add_sync(FULL, cnt);
+  if (lane == 0) *nc1_out = cnt;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ hash table (shared memory)
+__device__ __forceinline__ void table_insert(unsigned long long* keys, int* vals, int mask, uint64_t h, int v) {
+  int s = (int)(h & (uint64_t)mask);
+  for (;;) {
+    const unsigned long long old = atomicCAS(&keys[s], 0ull, (unsigned long long)h);
+    if (old == 0ull || old == (unsigned long long)h) {
+      vals[s] = v;
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+}
+__device__ __forceinline__ int table_find(const unsigned long long* keys, const int* vals, int mask, uint64_t h) {
+  if (h == 0ull) return -1;  // 0 marks an empty slot and "no parent"
+  int s = (int)(h & (uint64_t)mask);
+  for (;;) {
+    const unsigned long long k = keys[s];
+    if (k == (unsigned long long)h) return vals[s];
+    if (k == 0ull) return -1;
+    s = (s + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
+  SSD_DYN_SMEM(smem_raw);
+  unsigned char* sp = smem_raw;
+  const int W = P.W, VL = P.VL, TS = P.TS, NCAND = P.NCAND;
+
+  Prefix gen[2];
+  carve_prefix(sp, gen[0], W);
+  carve_prefix(sp, gen[1], W);
+  double* tot = (double*)carve(sp, 8 * W);
+  double* newb = (double*)carve(sp, 8 * W);
+  double* newnb = (double*)carve(sp, 8 * W);
+  double* ext_in = (double*)carve(sp, 8 * W);
+  int* par = (int*)carve(sp, 4 * W);
+  int* rnk = (int*)carve(sp, 4 * W);
+  int* rank2p = (int*)carve(sp, 4 * W);
+  int* rowoff = (int*)carve(sp, 4 * W);
+  int* keepf = (int*)carve(sp, 4 * W);
+  int* oslot = (int*)carve(sp, 4 * W);
+  unsigned long long* tkeys = (unsigned long long*)carve(sp, 8 * TS);
+  int* tvals = (int*)carve(sp, 4 * TS);
+  double* cscore = (double*)carve(sp, 8 * NCAND);
+  uint32_t* cdesc = (uint32_t*)carve(sp, 4 * NCAND);
+  double* ascore = (double*)carve(sp, 8 * NCAND);
+  int* aidx = (int*)carve(sp, 4 * NCAND);
+  int* sel = (int*)carve(sp, 4 * (W + 1));
+  int* sel_keep = (int*)carve(sp, 4 * (W + 1));
+  int* sel_slot = (int*)carve(sp, 4 * (W + 1));
+  uint64_t* sel_hk = (uint64_t*)carve(sp, 8 * (W + 1));
+  int* sel_lc = (int*)carve(sp, 4 * (W + 1));
+  FrameRec fr[2];
+  for (int i = 0; i < 2; ++i) {
+    fr[i].rl = (float*)carve(sp, 4 * VL);
+    fr[i].cs = (unsigned char*)carve(sp, VL);
+  }
+  int* lab2voc = (int*)carve(sp, 4 * VL);
+  float* chunk[2];
+  chunk[0] = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  chunk[1] = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  Scal* sc = (Scal*)carve(sp, sizeof(Scal));
+
+  const int tid = (int)threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == BM_CONS / 32;
+  const int tmask = TS - 1;
+  uint2* nodes = P.nodes + (int64_t)blockIdx.x * P.node_cap;
+  const int space_lbl_vocab = P.space;
+
+  // label <-> vocabulary id (ctc.py:64-65): label 0 = blank, then ids in order without blank/pad
+  if (tid == 0) {
+    int k = 1;
+    lab2voc[0] = P.blank;
+    for (int v = 0; v < P.V; ++v)
+      if (v != P.blank && v != P.pad) lab2voc[k++] = v;
+    mbar_init(&sc->bar[0], 1);
+    mbar_init(&sc->bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int space_lbl = -1;
+  for (int k = 1; k < VL; ++k)
+    if (lab2voc[k] == space_lbl_vocab) space_lbl = k;
+
+  unsigned tma_phase[2] = {0u, 0u};  // producer-side parity per chunk buffer
+
+  for (;;) {
+    // ---------------- fetch next utterance
+    if (tid == 0) sc->utt = (int)atomicAdd(P.counter, 1u);
+    __syncthreads();
+    const int u = sc->utt;
+    if (u >= P.B) break;
+    const int b = P.order ? P.order[u] : u;
+    int64_t len64 = P.lengths[b];
+    const int len = (int)(len64 < 0 ? 0 : (len64 > P.T ? P.T : len64));
+    const float* base = P.lp + (int64_t)b * P.sb;
+    const int nchunks = (len + BM_CHUNK - 1) / BM_CHUNK;
+
+    // ---------------- initial beam: the empty prefix, blank-ended with score 0
+    if (tid == 0) {
+      Prefix& a = gen[0];
+      a.H[0] = hmix(0x243F6A8885A308D3ull, 0u);
+      a.Hpar[0] = 0ull;  // never a key
+      a.Hstrip[0] = a.H[0];
+      a.hl[0] = 0ull;
+      a.ho[0] = 0ull;
+      a.sb[0] = 0.0;
+      a.snb[0] = neg_inf();
+      a.node[0] = 0u;
+      a.last[0] = space_lbl >= 0 ? space_lbl : LBL_NONE;  // a space after "" is absorbed
+      a.len[0] = 0;
+      sc->np = 1;
+      sc->nodes_used = 1u;
+      nodes[0] = make_uint2(0u, 0u);
+    }
+    for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
+    __syncthreads();
+    if (tid == 0) table_insert(tkeys, tvals, tmask, gen[0].H[0], 0);
+
+    // ---------------- producer prologue: chunk 0 (+1 in flight), frame 0 record
+    auto load_chunk = [&](int c) {  // producer warp
+      const int rows = min(BM_CHUNK, len - c * BM_CHUNK);
+      float* dst = chunk[c & 1];
+      const float* src = base + (int64_t)c * BM_CHUNK * P.st;
+      if (P.use_tma) {
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)(rows * P.V * 4);
+          mbar_arrive_expect_tx(&sc->bar[c & 1], bytes);
+          bulk_g2s(dst, src, bytes, &sc->bar[c & 1]);
+        }
+      } else {
+        for (int i = lane; i < rows * P.V; i += 32) {
+          const int r = i / P.V, v = i - r * P.V;
+          dst[i] = ld_stream(src + (int64_t)r * P.st + v);
+        }
+        __syncwarp();
+      }
+    };
+    auto wait_chunk = [&](int c) {
+      if (P.use_tma) {
+        mbar_wait(&sc->bar[c & 1], tma_phase[c & 1]);
+        tma_phase[c & 1] ^= 1u;
+      }
+    };
+    if (producer && len > 0) {
+      load_chunk(0);
+      if (nchunks > 1) load_chunk(1);
+      wait_chunk(0);
+      condition_frame(chunk[0], P, lab2voc, fr[0], &sc->nc1[0]);
+    }
+    __syncthreads();
+
+    int g = 0;  // current prefix generation
+    for (int t = 0; t < len; ++t) {
+      if (producer) {
+        // -------- condition frame t+1 while the consumers work on frame t
+        const int tn = t + 1;
+        if (tn < len) {
+          const int c = tn / BM_CHUNK, r = tn - c * BM_CHUNK;
+          if (r == 0) {
+            // chunk c-1 is fully consumed (its last frame was conditioned an iteration ago)
+            if (c + 1 < nchunks) load_chunk(c + 1);
+            wait_chunk(c);
+          }
+          condition_frame(chunk[c & 1] + r * P.V, P, lab2voc, fr[tn & 1], &sc->nc1[tn & 1]);
+        }
+        bar_sync(BAR_FRAME, BM_THREADS);
+        continue;
+      }
+      // ============================ consumers ============================
+      const Prefix& A = gen[g];
+      const Prefix& N = gen[g ^ 1];
+      const FrameRec F = fr[t & 1];
+      const int nc1 = sc->nc1[t & 1];
+      const int np = sc->np;
+      const unsigned node0 = sc->nodes_used;  // read here: thread 0 rewrites it in phase 6b
+      SSD_ASSERT(np >= 1 && np <= W);
+
+      // ---- phase 1: tot, parent slot
+      for (int p = tid; p < np; p += BM_CONS) {
+        tot[p] = lse2(A.sb[p], A.snb[p]);
+        par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 2: rank by tot; per-prefix entries
+      const float r_blank = F.rl[0];
+      for (int p = tid; p < np; p += BM_CONS) {
+        const double mine = tot[p];
+        int rk = 0;
+        for (int q = 0; q < np; ++q) {
+          const double o = tot[q];
+          rk += (o > mine || (o == mine && q < p)) ? 1 : 0;
+        }
+        rnk[p] = rk;
+        rank2p[rk] = p;
+        const int e = A.last[p];
+        const float r_e = (e != LBL_NONE) ? F.rl[e] : -INFINITY;
+        newb[p] = (r_blank != -INFINITY) ? mine + (double)r_blank : neg_inf();
+        double rep = neg_inf(), ext = neg_inf();
+        if (r_e != -INFINITY) {
+          // repeat of the last char keeps the text; an absorbed space also collects the blank-ended mass
+          rep = (e == space_lbl ? mine : A.snb[p]) + (double)r_e;
+          const int pp = par[p];
+          if (pp >= 0) ext = ((A.last[pp] != e) ? tot[pp] : A.sb[pp]) + (double)r_e;
+        }
+        newnb[p] = lse2(rep, ext);
+        // staircase width of this row
+        int J = W / (rk + 1) + 1;
+        rowoff[rk] = J < nc1 ? J : nc1;
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 2b: exclusive scan of row widths (warp 0)
+      if (warp == 0) {
+        int carry = 0;
+        for (int i0 = 0; i0 < np; i0 += 32) {
+          const int i = i0 + lane;
+          const int v = i < np ? rowoff[i] : 0;
+          int incl = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+          }
+          if (i < np) rowoff[i] = carry + incl - v;
+          carry += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) sc->n_e3 = carry;
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 3: candidate entries
+      const int n_e3 = sc->n_e3;
+      const int ncand = 2 * np + n_e3;
+      SSD_ASSERT(ncand <= NCAND);
+      for (int k = tid; k < ncand; k += BM_CONS) {
+        double s;
+        uint32_t d;
+        if (k < np) {
+          s = newb[k];
+          d = ((uint32_t)k << 8) | 0u;  // blank-ended entry of prefix k
+        } else if (k < 2 * np) {
+          const int p = k - np;
+          s = newnb[p];
+          d = ((uint32_t)p << 8) | 0xFEu;  // char-ended entry of prefix p
+        } else {
+          const int q = k - 2 * np;
+          int lo = 0, hi = np - 1;  // last row with rowoff <= q
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rowoff[mid] <= q) lo = mid; else hi = mid - 1;
+          }
+          const int p = rank2p[lo];
+          const int c = (int)F.cs[q - rowoff[lo]];
+          const int e = A.last[p];
+          s = neg_inf();
+          if (!(c == space_lbl && e == space_lbl)) {  // absorbed space is not an extension
+            const uint64_t h = hmix(A.H[p], (uint32_t)c);
+            if (table_find(tkeys, tvals, tmask, h) < 0)  // else folded into the live child's snb
+              s = ((c == e) ? A.sb[p] : tot[p]) + (double)F.rl[c];
+          }
+          d = ((uint32_t)p << 8) | (uint32_t)c;
+        }
+        cscore[k] = s;
+        cdesc[k] = d;
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 4a: block max
+      {
+        double m = neg_inf();
+        for (int k = tid; k < ncand; k += BM_CONS) m = cscore[k] > m ? cscore[k] : m;
+        m = warp_max_d(m);
+        if (lane == 0) sc->wmax[warp] = m;
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+      double cutoff;
+      {
+        double m = sc->wmax[0];
+        for (int w = 1; w < BM_CONS / 32; ++w) m = sc->wmax[w] > m ? sc->wmax[w] : m;
+        cutoff = m + (double)P.prune;
+      }
+      // ---- phase 4b: compact entries that survive the relative prune (order preserved)
+      {
+        int base_k = 0;
+        int running = 0;
+        for (; base_k < ncand; base_k += BM_CONS) {
+          const int k = base_k + tid;
+          const bool alive = k < ncand && cscore[k] >= cutoff && cscore[k] != -INFINITY;
+          const unsigned m = __ballot_sync(FULL, alive);
+          if (lane == 0) sc->wcnt[warp] = __popc(m);
+          bar_sync(BAR_CONS, BM_CONS);
+          int off = running, totc = 0;
+#pragma unroll
+          for (int w = 0; w < BM_CONS / 32; ++w) {
+            const int c = sc->wcnt[w];
+            if (w < warp) off += c;
+            totc += c;
+          }
+          if (alive) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            ascore[pos] = cscore[k];
+            aidx[pos] = k;
+          }
+          running += totc;
+          bar_sync(BAR_CONS, BM_CONS);
+        }
+        if (tid == 0) sc->n_alive = running;
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+      const int n_alive = sc->n_alive;
+      const int n_sel = n_alive < W ? n_alive : W;
+      // ---- phase 4c: exact rank among the alive; the W best go to sel[rank]
+      for (int i = tid; i < n_alive; i += BM_CONS) {
+        const double mine = ascore[i];
+        int rk = 0;
+        for (int j = 0; j < n_alive; ++j) {
+          const double o = ascore[j];
+          rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
+        }
+        if (rk < W) sel[rk] = aidx[i];
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 5: history keys, then keep the best entry per key
+      for (int r = tid; r < n_sel; r += BM_CONS) {
+        const uint32_t d = cdesc[sel[r]];
+        const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
+        uint64_t hl = A.hl[p], ho = A.ho[p];
+        int lc;
+        if (c == 0) lc = 0;
+        else if (c == 0xFE) lc = A.last[p];
+        else {
+          lc = c;
+          if (c == space_lbl) { hl = ho; ho = 0ull; }
+          else ho = hmix(ho, (uint32_t)c);
+        }
+        sel_hk[r] = hmix(hl ^ hmix(ho, 0x5bu), 0xa7u);
+        sel_lc[r] = lc;
+      }
+      for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
+      bar_sync(BAR_CONS, BM_CONS);
+      for (int r = tid; r < n_sel; r += BM_CONS) {
+        const uint64_t hk = sel_hk[r];
+        const int lc = sel_lc[r];
+        int keep = 1;
+        for (int q = 0; q < r; ++q)
+          if (sel_hk[q] == hk && sel_lc[q] == lc) { keep = 0; break; }
+        const uint32_t d = cdesc[sel[r]];
+        const int c = (int)(d & 0xFFu);
+        if (keep && (c == 0 || c == 0xFE)) {
+          atomicOr(&keepf[d >> 8], c == 0 ? 1 : 2);
+          keep = 0;  // lives on inside an existing prefix, no new slot
+          sel_keep[r] = 0;
+        } else {
+          sel_keep[r] = keep;
+        }
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 6a: slots.  warp 0 scans surviving old prefixes, warp 1 the new ones.
+      if (warp == 0) {
+        int carry = 0;
+        for (int i0 = 0; i0 < np; i0 += 32) {
+          const int i = i0 + lane;
+          const bool f = i < np && keepf[i] != 0;
+          const unsigned m = __ballot_sync(FULL, f);
+          if (i < np) oslot[i] = f ? carry + __popc(m & ((1u << lane) - 1u)) : -1;
+          carry += __popc(m);
+        }
+        if (lane == 0) sc->n_keep_old = carry;
+      } else if (warp == 1) {
+        int carry = 0;
+        for (int i0 = 0; i0 < n_sel; i0 += 32) {
+          const int i = i0 + lane;
+          const bool f = i < n_sel && sel_keep[i] != 0;
+          const unsigned m = __ballot_sync(FULL, f);
+          if (i < n_sel) sel_slot[i] = f ? carry + __popc(m & ((1u << lane) - 1u)) : -1;
+          carry += __popc(m);
+        }
+        if (lane == 0) sc->n_new = carry;
+      }
+      for (int i = tid; i < TS; i += BM_CONS) tkeys[i] = 0ull;
+      bar_sync(BAR_CONS, BM_CONS);
+
+      // ---- phase 6b: write the next generation and its hash table
+      const int n_old = sc->n_keep_old, n_new = sc->n_new;
+      SSD_ASSERT(n_old + n_new >= 1 && n_old + n_new <= W);
+      for (int p = tid; p < np; p += BM_CONS) {
+        const int s = oslot[p];
+        if (s < 0) continue;
+        N.H[s] = A.H[p]; N.Hpar[s] = A.Hpar[p]; N.Hstrip[s] = A.Hstrip[p];
+        N.hl[s] = A.hl[p]; N.ho[s] = A.ho[p];
+        N.node[s] = A.node[p]; N.last[s] = A.last[p]; N.len[s] = A.len[p];
+        N.sb[s] = (keepf[p] & 1) ? newb[p] : neg_inf();
+        N.snb[s] = (keepf[p] & 2) ? newnb[p] : neg_inf();
+        table_insert(tkeys, tvals, tmask, A.H[p], s);
+      }
+      for (int r = tid; r < n_sel; r += BM_CONS) {
+        const int j = sel_slot[r];
+        if (j < 0) continue;
+        const int s = n_old + j;
+        const int k = sel[r];
+        const uint32_t d = cdesc[k];
+        const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
+        const uint64_t h = hmix(A.H[p], (uint32_t)c);
+        N.H[s] = h; N.Hpar[s] = A.H[p];
+        if (c == space_lbl) { N.Hstrip[s] = A.H[p]; N.hl[s] = A.ho[p]; N.ho[s] = 0ull; }
+        else { N.Hstrip[s] = h; N.hl[s] = A.hl[p]; N.ho[s] = hmix(A.ho[p], (uint32_t)c); }
+        N.last[s] = c; N.len[s] = A.len[p] + 1;
+        N.sb[s] = neg_inf(); N.snb[s] = cscore[k];
+        const unsigned nd = node0 + (unsigned)j;
+        SSD_ASSERT((int64_t)nd < P.node_cap);
+        N.node[s] = nd;
+        nodes[nd] = make_uint2(A.node[p], (unsigned)c);
+        table_insert(tkeys, tvals, tmask, h, s);
+      }
+      if (tid == 0) {
+        sc->np = n_old + n_new;
+        sc->nodes_used = node0 + (unsigned)n_new;
+      }
+      g ^= 1;
+      bar_sync(BAR_FRAME, BM_THREADS);  // next generation, table, and frame t+1 record are all visible
+    }
+
+    // ---------------- finish: merge variants, pick the best text, emit labels
+    __syncthreads();
+    if (!producer) {
+      const Prefix& A = gen[g];
+      const int np = sc->np;
+      for (int p = tid; p < np; p += BM_CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
+      bar_sync(BAR_CONS, BM_CONS);
+      for (int p = tid; p < np; p += BM_CONS) {
+        // group = prefixes with equal text after dropping a trailing space
+        const uint64_t hs = A.Hstrip[p];
+        double f = neg_inf();
+        int rep = p;
+        for (int q = 0; q < np; ++q)
+          if (A.Hstrip[q] == hs) {
+            f = lse2(f, tot[q]);
+            if (q < rep) rep = q;
+          }
+        newb[p] = (rep == p) ? f : neg_inf();  // one representative per group competes
+      }
+      bar_sync(BAR_CONS, BM_CONS);
+      if (tid == 0) {
+        int best = 0;
+        for (int p = 1; p < np; ++p)
+          if (newb[p] > newb[best]) best = p;
+        int n = A.len[best];
+        unsigned nd = A.node[best];
+        int32_t* out = P.out_tok + (int64_t)b * P.T;
+        if (n > 0 && A.last[best] == space_lbl) {  // trailing space is not part of the text
+          nd = nodes[nd].x;
+          --n;
+        }
+        P.out_len[b] = n;
+        if (P.out_score) P.out_score[b] = len > 0 ? newb[best] : 0.0;
+        for (int i = n - 1; i >= 0; --i) {
+          const uint2 rec = nodes[nd];
+          out[i] = lab2voc[rec.y];
+          nd = rec.x;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int beam_grid(int64_t B, size_t smem) {
+#ifdef SSD_EMU
+  (void)smem;
+  return (int)(B < 3 ? B : 3);
+#else
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, BM_THREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int64_t g = (int64_t)sms * per_sm;
+  return (int)(B < g ? B : g);
+#endif
+}
+
+static int beam_vl(int64_t V, int blank, int pad) { return (int)V - 1 - ((pad >= 0 && pad < V && pad != blank) ? 1 : 0) + 1; }
+
+static int64_t beam_node_cap(int64_t T, int W) { return T * (int64_t)W + 2; }
+
+static int beam_max_grid() {
+#ifdef SSD_EMU
+  return 3;
+#else
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * 8;
+#endif
+}
+
+size_t beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int width) {
+  (void)V;
+  int64_t g = beam_max_grid();
+  if (B < g) g = B;
+  return 256 + (size_t)g * (size_t)beam_node_cap(T, width) * sizeof(uint2);
+}
+
+int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths,
+                const int32_t* order, int blank, int pad, int space, float bias, int width, float prune, float tmin,
+                int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (B == 0) return SSD_OK;
+  BeamParams P;
+  P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
+  P.lengths = lengths; P.order = order;
+  P.blank = blank; P.pad = (pad >= 0 && pad < V) ? pad : -1; P.space = space;
+  P.bias = bias; P.prune = prune; P.tmin = tmin; P.W = width;
+  P.out_tok = out_tok; P.out_len = out_len; P.out_score = out_score;
+  P.VL = beam_vl(V, blank, P.pad);
+  P.TS = beam_table_slots(width);
+  P.NCAND = beam_ncand_cap(width, P.VL);
+  P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
+  const size_t smem = beam_smem_bytes(width, (int)V, P.VL, P.TS, P.NCAND);
+  if (smem > 227 * 1024) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
+#ifndef SSD_EMU
+  cudaError_t e = cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+#endif
+  int grid = beam_grid(B, smem);
+  const int gmax = beam_max_grid();
+  if (grid > gmax) grid = gmax;
+  P.node_cap = beam_node_cap(T, width);
+  const size_t need = 256 + (size_t)grid * (size_t)P.node_cap * sizeof(uint2);
+  if (!ws || ws_bytes < need) return fail(SSD_ERR_WORKSPACE, "beam: workspace %zu bytes, need %zu", ws_bytes, need);
+  P.counter = reinterpret_cast<unsigned*>(ws);
+  P.nodes = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(ws) + 256);
+#ifdef SSD_EMU
+  *P.counter = 0u;
+#else
+  e = cudaMemsetAsync(P.counter, 0, 256, stream);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaMemsetAsync: %s", cudaGetErrorString(e));
+#endif
+  SSD_LAUNCH(beam_kernel, (unsigned)grid, BM_THREADS, smem, stream, P);
+  return check_launch("beam_kernel");
+}
+
+}  // namespace ssd

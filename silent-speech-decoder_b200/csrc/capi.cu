@@ -1,0 +1,81 @@
+// extern "C" entry points of libssd_ctc.so: argument validation, then one kernel launch each.
+// Declared in include/ssd_ctc.h.
+#include "ssd_common.cuh"
+
+namespace ssd {
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+}  // namespace ssd
+
+using namespace ssd;
+
+static int check_common(const char* fn, const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st) {
+  if (B < 0 || T < 0 || V <= 0) return fail(SSD_ERR_BAD_ARG, "%s: negative or zero dimension (B=%lld T=%lld V=%lld)", fn, (long long)B, (long long)T, (long long)V);
+  if (V > SSD_MAX_VOCAB) return fail(SSD_ERR_UNSUPPORTED, "%s: V=%lld exceeds SSD_MAX_VOCAB=%d", fn, (long long)V, SSD_MAX_VOCAB);
+  if (B > 0 && T > 0 && !lp) return fail(SSD_ERR_BAD_ARG, "%s: log_probs is NULL", fn);
+  if (st < V && T > 1) return fail(SSD_ERR_BAD_ARG, "%s: stride_t=%lld < V=%lld (vocabulary must be contiguous)", fn, (long long)st, (long long)V);
+  if (sb < 0 || st < 0) return fail(SSD_ERR_BAD_ARG, "%s: negative stride", fn);
+  if (B > 2147483647LL || T > 2147483647LL / (V > 0 ? V : 1)) return fail(SSD_ERR_UNSUPPORTED, "%s: B or T*V exceeds 32-bit range", fn);
+  return SSD_OK;
+}
+
+extern "C" {
+
+int ssd_abi_version(void) { return SSD_ABI_VERSION; }
+const char* ssd_last_error(void) { return error_buffer(); }
+
+int ssd_ctc_greedy(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                   const int64_t* lengths, int blank, float blank_bias, int32_t* out_tokens, int32_t* out_lengths,
+                   void* stream) {
+  int rc = check_common("ssd_ctc_greedy", log_probs, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (B > 0 && (!lengths || !out_lengths || (T > 0 && !out_tokens))) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_greedy: NULL lengths/output pointer");
+  // blank outside [0,V) is legal for the reference (no id ever equals it); keep that behaviour
+  return greedy_launch(log_probs, B, T, V, stride_b, stride_t, lengths, blank, blank_bias, out_tokens, out_lengths, (cudaStream_t)stream);
+}
+
+size_t ssd_ctc_beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int beam_width) {
+  if (B <= 0 || T < 0 || V <= 0 || beam_width <= 0) return 256;
+  return beam_workspace_bytes(B, T, V, beam_width);
+}
+
+int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                 const int64_t* lengths, const int32_t* order, int blank, int pad, int space, float blank_bias,
+                 int beam_width, float beam_prune_logp, float token_min_logp, int32_t* out_tokens,
+                 int32_t* out_lengths, double* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("ssd_ctc_beam", log_probs, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (B > 0 && (!lengths || !out_lengths || (T > 0 && !out_tokens))) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: NULL lengths/output pointer");
+  if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: blank=%d outside [0,%lld)", blank, (long long)V);
+  if (beam_width < 1 || beam_width > SSD_MAX_BEAM) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam: beam_width=%d outside [1,%d]", beam_width, SSD_MAX_BEAM);
+  if (!(beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: beam_prune_logp must be <= 0");
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, blank_bias, beam_width,
+                     beam_prune_logp, token_min_logp, out_tokens, out_lengths, out_scores, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+size_t ssd_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
+  if (B <= 0 || T < 0 || V <= 0 || S_max < 0) return 256;
+  return loss_workspace_bytes(B, T, V, S_max);
+}
+
+int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                 const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
+                 const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
+                 int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  int rc = check_common("ssd_ctc_loss", log_probs, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (B > 0 && (!input_lengths || !target_lengths || !nll)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: NULL lengths/nll pointer");
+  if (S_max < 0 || (S_max > 0 && B > 0 && !targets)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: bad targets (S_max=%lld)", (long long)S_max);
+  if (S_max > SSD_MAX_TARGET) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_loss: S_max=%lld exceeds SSD_MAX_TARGET=%d", (long long)S_max, SSD_MAX_TARGET);
+  if (tgt_stride < S_max) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: tgt_stride < S_max");
+  if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: blank=%d outside [0,%lld)", blank, (long long)V);
+  if (mean_denominator < 0) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: mean_denominator < 0");
+  return loss_launch(log_probs, B, T, V, stride_b, stride_t, targets, tgt_stride, S_max, input_lengths, target_lengths, order, blank,
+                     zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and launch checks.
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ssd_ctc.h"
+#include "ssd_dev.cuh"
+
+namespace ssd {
+
+char* error_buffer();  // thread-local, defined in capi.cu
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SSD_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Entry points implemented one per translation unit.
+int greedy_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths, int blank,
+                  float bias, int32_t* out_tok, int32_t* out_len, cudaStream_t stream);
+
+size_t beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int width);
+int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths,
+                const int32_t* order, int blank, int pad, int space, float bias, int width, float prune, float tmin,
+                int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
+                int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
+                int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
+                size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace ssd

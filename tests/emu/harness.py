@@ -1,0 +1,99 @@
+"""Builds and drives the EMULATED kernel library (tests only).
+
+``libssd_ctc_emu.so`` is the product's kernel sources compiled by g++ with -DSSD_EMU against
+tests/emu/ssd_emu.h.  It lets the CPU-only test tier execute kernel logic; it is not part of
+the product and nothing under silent-speech-decoder_b200/ refers to it.
+"""
+
+from __future__ import annotations
+
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+CSRC = REPO / "silent-speech-decoder_b200" / "csrc"
+OUT = HERE / "_build"
+LIB = OUT / "libssd_ctc_emu.so"
+SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "capi.cu"]
+
+
+def build(force: bool = False) -> Path:
+    OUT.mkdir(exist_ok=True)
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE / "ssd_emu.h", REPO / "include" / "ssd_ctc.h"]
+    if not force and LIB.exists() and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
+        return LIB
+
+    def cc(src):
+        obj = OUT / (Path(src).stem + ".o")
+        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-DSSD_EMU", "-I", str(HERE), "-I", str(CSRC), "-x", "c++", "-c",
+               str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(f"g++ failed on {src}:\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(4) as ex:
+        objs = list(ex.map(cc, SOURCES))
+    r = subprocess.run(["g++", "-shared", "-o", str(LIB), *map(str, objs)], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError(r.stderr)
+    return LIB
+
+
+def library():
+    from silent_speech_decoder_b200._native import Library
+
+    return Library(build())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def greedy(lib, lp: np.ndarray, lengths, blank: int, bias: float = 0.0):
+    lp = np.ascontiguousarray(lp, dtype=np.float32)
+    B, T, V = lp.shape
+    ln = np.asarray(lengths, dtype=np.int64)
+    tok = np.full((B, max(T, 1)), -7, dtype=np.int32)
+    n = np.full((B,), -7, dtype=np.int32)
+    lib.check(lib.ssd_ctc_greedy(_ptr(lp), B, T, V, T * V, V, _ptr(ln), blank, bias, _ptr(tok), _ptr(n), None))
+    return [[int(x) for x in tok[b, : n[b]]] for b in range(B)]
+
+
+def beam(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, width: int = 50, prune: float = -10.0,
+         bias: float = 0.0, tmin: float = -5.0, order=None):
+    lp = np.ascontiguousarray(lp, dtype=np.float32)
+    B, T, V = lp.shape
+    ln = np.asarray(lengths, dtype=np.int64)
+    tok = np.full((B, max(T, 1)), -7, dtype=np.int32)
+    n = np.full((B,), -7, dtype=np.int32)
+    sc = np.full((B,), np.nan, dtype=np.float64)
+    nbytes = lib.ssd_ctc_beam_workspace_bytes(B, T, V, width)
+    ws = np.zeros(nbytes // 8 + 1, dtype=np.int64)
+    od = None if order is None else np.asarray(order, dtype=np.int32)
+    lib.check(lib.ssd_ctc_beam(_ptr(lp), B, T, V, T * V, V, _ptr(ln), _ptr(od), blank, pad, space, bias, width, prune, tmin,
+                               _ptr(tok), _ptr(n), _ptr(sc), _ptr(ws), ws.nbytes, None))
+    return [[int(x) for x in tok[b, : n[b]]] for b in range(B)], sc
+
+
+def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity: bool = True, mean_den: int = 0,
+         want_grad: bool = True, grad_mul=None):
+    lp = np.ascontiguousarray(lp, dtype=np.float32)
+    B, T, V = lp.shape
+    il = np.asarray(in_len, dtype=np.int64)
+    tl = np.asarray(tg_len, dtype=np.int64)
+    tg = np.ascontiguousarray(targets, dtype=np.int64).reshape(B, -1)
+    S = tg.shape[1]
+    nll = np.full((B,), np.nan, dtype=np.float32)
+    grad = np.full_like(lp, np.nan) if want_grad else None
+    nbytes = lib.ssd_ctc_loss_workspace_bytes(B, T, V, S)
+    ws = np.zeros(nbytes // 8 + 1, dtype=np.int64)
+    gm = None if grad_mul is None else np.asarray([grad_mul], dtype=np.float32)
+    lib.check(lib.ssd_ctc_loss(_ptr(lp), B, T, V, T * V, V, _ptr(tg), S, S, _ptr(il), _ptr(tl), None, blank, int(zero_infinity),
+                               mean_den, _ptr(gm), _ptr(nll), _ptr(grad), _ptr(ws), ws.nbytes, None))
+    return nll, grad
