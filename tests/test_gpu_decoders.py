@@ -1,0 +1,149 @@
+"""GPU parity tests for the greedy and beam kernels, called through the C ABI (via the
+reference-shaped Python API).  Oracles: oracle/greedy.py (pinned to the reference) and
+oracle/beam.py (restatement of pyctcdecode, UNPINNED)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beam as ob
+from oracle import greedy as og
+from silent_speech_decoder_b200 import ops, synth
+from silent_speech_decoder_b200.data.vocab import Vocab
+from silent_speech_decoder_b200.decoding import ctc
+
+pytestmark = pytest.mark.gpu
+V = Vocab.default()
+SCORE_ATOL = 1e-4  # north_star: beam prefix scores within 1e-4 absolute
+
+
+def _unragged(arr):
+    return [[int(x) for x in row if x >= 0] for row in arr]
+
+
+# ------------------------------------------------------------------ greedy
+def test_greedy_known_answer_vector(golden_dir):
+    z = np.load(os.path.join(golden_dir, "greedy_ref.npz"))
+    got = ctc._greedy_decode(torch.from_numpy(z["kat.lp"]), torch.tensor([5, 5]), blank_id=0)
+    assert got == [[1, 2], [1, 2]]
+
+
+@pytest.mark.parametrize("name", ["flat", "peaked", "peaked_bias", "flat_negbias"])
+def test_greedy_matches_reference_outputs(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "greedy_ref.npz"))
+    lp, ln, bias = torch.from_numpy(z[f"{name}.lp"]), torch.from_numpy(z[f"{name}.len"]), float(z[f"{name}.bias"])
+    assert ctc._greedy_decode(lp, ln, V.blank_id, bias) == _unragged(z[f"{name}.ids"])
+    assert ctc.build_greedy_decoder(V, blank_bias=bias)(lp.cuda(), ln.cuda()) == list(z[f"{name}.text"])
+
+
+def test_greedy_cfg1(golden_dir):
+    z = np.load(os.path.join(golden_dir, "cfg1_ref.npz"))
+    lp, ln = torch.from_numpy(z["lp"]), torch.from_numpy(z["il"])
+    assert ctc._greedy_decode(lp, ln, 1) == _unragged(z["greedy_ids"])
+    assert ctc.build_decoder("greedy", V)(lp, ln) == list(z["greedy_text"])
+
+
+@pytest.mark.parametrize("B,T,gen", [(64, 500, "flat"), (64, 500, "peaked"), (3, 4000, "peaked"), (257, 129, "flat")])
+def test_greedy_vs_oracle(B, T, gen):
+    lp = getattr(synth, gen)(B, T, 31 + B + T)
+    ln = synth.ragged_lengths(B, T, 7)
+    ln[0] = T
+    ln[-1] = 0
+    assert ctc._greedy_decode(lp, ln, V.blank_id) == og.greedy_ids(lp.numpy(), ln.tolist(), V.blank_id)
+
+
+def test_greedy_strided_and_odd_vocab():
+    # non-contiguous batch/time strides and a vocabulary that defeats the TMA path (V*4 % 16 != 0)
+    g = torch.Generator().manual_seed(5)
+    big = torch.log_softmax(torch.randn(6, 70, 37, generator=g), -1)
+    lp = big[::2, 3:63]  # (3,60,37), strides (2*70*37, 37, 1)
+    ln = torch.tensor([60, 41, 1])
+    want = og.greedy_ids(lp.contiguous().numpy(), ln.tolist(), 0)
+    assert ctc._greedy_decode(lp.cuda(), ln, 0) == want
+    tv = torch.log_softmax(torch.randn(50, 4, 48, generator=g), -1)  # (T,B,V) storage viewed as (B,T,V)
+    view = tv.transpose(0, 1)
+    assert ctc._greedy_decode(view.cuda(), torch.tensor([50, 50, 20, 50]), 1) == og.greedy_ids(
+        view.contiguous().numpy(), [50, 50, 20, 50], 1)
+
+
+def test_greedy_full_size_property():
+    # cfg3 shape: 10k x 500 x 48.  Property: decoding is invariant to frame duplication
+    # (every frame doubled collapses to the same ids) and never emits blank.
+    lp = synth.flat(2000, 500, 99).cuda()
+    ln = torch.full((2000,), 500)
+    a = ctc._greedy_decode(lp, ln, V.blank_id)
+    b = ctc._greedy_decode(lp.repeat_interleave(2, dim=1), ln * 2, V.blank_id)
+    assert a == b
+    assert all(V.blank_id not in s for s in a)
+
+
+# ------------------------------------------------------------------ beam
+def _oracle(lp, ln, width=50, prune=-10.0, bias=0.0):
+    return ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, bias).decode_with_scores(lp, ln)
+
+
+def _native(lp, ln, width=50, prune=-10.0, bias=0.0):
+    text = ctc.build_beam_decoder(V, None, width, beam_prune_logp=prune, blank_bias=bias)(lp, ln)
+    _, space = ctc._beam_label_strings(V)
+    _, _, score = ops.beam_ids(lp, ln, V.blank_id, V.pad_id, space, width, prune, bias)
+    return text, score.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["peaked50", "flat50", "flat20_bias", "peaked100_p12", "flat1", "flat200"])
+def test_beam_frozen_restatement(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "beam_restatement.npz"))
+    width, prune, bias = z[f"{name}.cfg"]
+    text, score = _native(torch.from_numpy(z[f"{name}.lp"]), torch.from_numpy(z[f"{name}.len"]), int(width), float(prune), float(bias))
+    assert text == list(z[f"{name}.text"])
+    assert np.abs(score - z[f"{name}.score"]).max() <= SCORE_ATOL
+
+
+def test_beam_cfg1(golden_dir):
+    z = np.load(os.path.join(golden_dir, "cfg1_ref.npz"))
+    text, score = _native(torch.from_numpy(z["lp"]), torch.from_numpy(z["il"]))
+    assert text == list(z["beam_text"])
+    assert np.abs(score - z["beam_score"]).max() <= SCORE_ATOL
+
+
+@pytest.mark.parametrize("gen,B,T,width", [("peaked", 24, 500, 50), ("flat", 6, 500, 50), ("peaked", 8, 300, 10),
+                                            ("flat", 4, 200, 100), ("peaked", 2, 1500, 200), ("flat", 8, 120, 1)])
+def test_beam_vs_oracle(gen, B, T, width):
+    lp = getattr(synth, gen)(B, T, 1003 + T + width)
+    ln = synth.ragged_lengths(B, T, 17).tolist()
+    ln[0] = T
+    want = _oracle(lp.numpy(), ln, width)
+    text, score = _native(lp, torch.tensor(ln), width)
+    assert text == [t for t, _ in want]
+    assert np.abs(score - np.array([s for _, s in want])).max() <= SCORE_ATOL
+
+
+def test_beam_edges():
+    dec = ctc.build_decoder("beam", V, beam_width=50)
+    lp = torch.full((3, 6, 48), -20.0)
+    lp[0, :, V.unk_id] = 0.0                       # unk renders as U+2047 on the beam path
+    lp[1, :, V.token_to_id[" "]] = 0.0             # only spaces -> empty text
+    lp[2, :3, V.token_to_id["a"]] = 0.0
+    lp[2, 3:, V.pad_id] = 0.0                      # pad mass behaves as blank
+    assert dec(lp, torch.tensor([6, 6, 6])) == [ob.UNK_GLYPH, "", "a"]
+    assert dec(lp, torch.tensor([0, 0, 0])) == ["", "", ""]
+    with pytest.raises(NotImplementedError):
+        ctc.build_decoder("beam", V, lm_path="lm.arpa")
+    with pytest.raises(ValueError):
+        dec(torch.zeros(1, 4, 47), torch.tensor([4]))
+
+
+def test_beam_full_size_properties():
+    # cfg3 scale (1/5 of it to bound oracle-free runtime): order independence and determinism
+    lp = synth.peaked(2000, 500, 1003).cuda()
+    ln = synth.ragged_lengths(2000, 500, 3).cuda()
+    dec = ctc.build_decoder("beam", V, beam_width=50)
+    a = dec(lp, ln)
+    perm = torch.randperm(2000, generator=torch.Generator().manual_seed(1)).cuda()
+    b = dec(lp[perm], ln[perm])
+    assert [a[i] for i in perm.tolist()] == b
+    assert dec(lp, ln) == a
+    # on sharply peaked input the best beam is the collapsed argmax path
+    g = ctc.build_decoder("greedy", V)(lp, ln)
+    agree = sum(x == " ".join(y.split()) for x, y in zip(a, g))
+    assert agree >= 0.95 * len(a)
