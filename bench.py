@@ -53,11 +53,13 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def recorded_traffic(kernel: str):
-    """dram bytes per launch from the committed ncu capture, if any (profiles/traffic.json)."""
+def recorded_traffic(kernel: str, frames: int):
+    """dram bytes per launch (read+write) from the committed ncu capture, scaled to this launch's
+    frame count (profiles/traffic.json holds bytes per frame), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            rec = json.load(f).get(kernel)
+        return None if rec is None else rec["bytes_per_frame"] * frames
     except Exception:
         return None
 
@@ -308,7 +310,7 @@ def bench_loss(args, rank, world, dev):
                    "l2": f"{nsets} rotating input/gradient sets = {nsets * 2 * B * T * V * 4 / 1e6:.0f} MB > 126 MB L2",
                    "parallelism": f"dp{world} by utterance, 2-scalar all-reduce of the loss"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic("loss_kernel"), "peak_source": peak_src, "kernel": "ssd::loss_kernel<double>",
+                     "traffic": recorded_traffic("loss_kernel", B * T), "peak_source": peak_src, "kernel": "ssd::loss_kernel<double>",
                      "kernel_ms": k_ms, "algorithmic_bytes": LOSS_BYTES_PER_FRAME * B * T},
         "e2e": {"value": world * B * T / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "api": "DistillationCTCLoss(...)(log_probs, ...)['total'].backward()"},
@@ -376,7 +378,7 @@ def bench_decode(args, rank, world, dev, method: str):
                    "l2": f"input {n_local * c['T'] * 48 * 4 / 1e6:.0f} MB > 126 MB L2",
                    "parallelism": f"dp{world} by utterance, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(kname), "peak_source": peak_src, "kernel": f"ssd::{kname}", "kernel_ms": ms,
+                     "traffic": recorded_traffic(kname + (("_" + args.beam_input) if method == "beam" else ""), n_local * c["T"]), "peak_source": peak_src, "kernel": f"ssd::{kname}", "kernel_ms": ms,
                      "algorithmic_bytes": DECODE_BYTES_PER_FRAME * n_local * c["T"],
                      "note": "beam search is latency/issue bound, not HBM bound; see profiles/ for stall breakdown" if method == "beam" else ""},
         "e2e": {"value": world * n_local / (e2e_ms * 1e-3), "unit": "utterances/s", "h2d_bytes_per_step": h_lp.numel() * 4 + h_ln.numel() * 8,
