@@ -3,31 +3,33 @@
 // Replaces torch.nn.CTCLoss as called at reference src/models/losses.py:56 (ATen ctc_loss + its
 // autograd backward).  See DESIGN.md section 4 for the derivation and the roofline discussion.
 //
-// Numerics.  The alpha/beta recursions run in the LINEAR domain on scaled fp64 values
-//   x_t[s] = (x_{t-1}[s] + x_{t-1}[s-1] + skip[s] * x_{t-1}[s-2]) * p_t[l'_s]
-// with an exact power-of-two rescale every few frames and the exponent tracked as an integer.
-// No exp/log sits on the recursion (ATen's log-space form needs 3-4 MUFU ops per cell) and the
-// result is accurate to ~1e-13, whereas fp32 log-space loses ~1e-3 of the gradient at T=1000.
-// p = expf(lp) is evaluated once per (frame, label) in fp32 and widened.
+// Numerics.  The alpha/beta recursions run in the LINEAR domain on fp64 values
+//   alpha_t[s] = (alpha_{t-1}[s] + alpha_{t-1}[s-1] + skip[s] * alpha_{t-1}[s-2]) * p_t[l'_s]
+// (beta: the mirror image, pulling from s+1, s+2).  A lane owns NC consecutive lattice cells in
+// registers together with ONE integer exponent for them (block floating point per lane); every 4
+// frames the lane renormalises its strip by an exact power of two.  Nothing on the recursion needs
+// exp/log (ATen's log-space form costs 3-4 MUFU ops per cell) and there is no global dynamic
+// range limit: cells may differ by thousands of binades across the lattice.  p = exp(lp) is
+// evaluated once per (frame, label) with an fp32 mantissa and a full fp64 exponent.
 //
-// Parallel structure (one CTA = 4 warps per utterance, CTAs pull utterances from a queue):
-//   warp 0  F-main   forward sweep  (alpha), local time tau = t
-//   warp 1  R-main   backward sweep (beta),  local time tau = T-1-t  -- by the symmetry of CTC this
-//                    is the same recursion on the reversed label sequence
-//   warp 2/3 helpers, one per main: producer side of a two-stage mbarrier pipeline.
-// A lane keeps NC consecutive lattice cells in registers; one shuffle per frame moves the strip
-// boundary.  The two sweeps MEET IN THE MIDDLE: each main first runs half of the frames
-// (phase 1), checkpointing its strip every K frames to an L2-resident workspace, then continues
-// through the other half (phase 2) where it needs the other sweep's values frame by frame.
-// Those are re-computed K frames at a time from the checkpoints by the main's helper (which
-// therefore runs the *other* direction's recursion) into shared memory, so alpha and beta are
-// never materialised in HBM: traffic is log_probs once + gradient once + (1/K) checkpoint spill.
-// In phase 2 a main multiplies its fresh x by the helper's pre-emission sums to get the lattice
-// posteriors, reduces them per label class (blank: warp shuffle; others: label-sorted staging in
-// shared memory) and writes the gradient row  scale * (p - posterior)  straight to HBM.
-//
-// Log-prob rows reach shared memory through 1-D TMA bulk copies (cp.async.bulk + mbarrier,
-// SASS UBLKCP) issued 3 segments ahead by the helpers, which also do the exp() conversion.
+// Parallel structure: one CTA of 8 warps per utterance (CTAs pull utterances from a queue).
+// The two sweeps MEET IN THE MIDDLE.  Per direction d in {forward, backward} ("half"):
+//   M  main      runs sweep d over all T frames: first its own half of the frames (phase 1,
+//                checkpointing its strip every K frames to an L2-resident workspace), then the
+//                other half (phase 2), where it multiplies its fresh values with the OTHER sweep's
+//                pre-emission sums to get lattice posteriors and stages them for G
+//   H  helper    phase 2 only: re-computes the other sweep K frames at a time from its checkpoints
+//                into shared memory (upper 32 bits of each fp64 sum + the per-lane exponents), one
+//                segment ahead of M
+//   L  loader    issues 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) of the next
+//                log-prob rows 3 segments ahead and converts them to probabilities for M, H and G
+//   G  gradient  one segment behind M: per frame reduces the staged posteriors per label class
+//                (blank: shuffle reduce; labels: staging is sorted by class, so one warp prefix
+//                scan gives every class sum as a difference) and writes  scale * (p - posterior)
+// Alpha and beta are never materialised in HBM: traffic is log_probs once + gradient once +
+// the 1/K checkpoint spill.  All hand-offs are mbarrier full/empty pairs; no __syncthreads in
+// the frame loop.  Every waiter of a barrier is also part of the chain that lets it complete
+// again (or has a barrier of its own), so a parity can never alias.
 #include <cmath>
 #include <cstdlib>
 
@@ -35,35 +37,38 @@
 
 namespace ssd {
 
-constexpr int LS_THREADS = 128;
+constexpr int LS_THREADS = 256;
 constexpr int LS_NRAW = 4;     // raw-row ring depth per half (TMA prefetch distance = 3 segments)
-constexpr int LS_RESCALE = 4;  // frames between rescale checks
+constexpr int LS_NP = 4;       // probability-row ring depth per half
+constexpr int LS_RESCALE = 4;  // frames between strip renormalisations
+constexpr int E_ADOPT = 200;   // incoming exponent this far above mine: rebase my strip instead
+constexpr int E_NONE = -(1 << 30);
 
 // ------------------------------------------------------------------ scalar helpers
-template <typename R>
-struct Fp;
-template <>
-struct Fp<double> {
-  static constexpr int WINDOW = 256;
-  static __device__ __forceinline__ int hi(double v) { return __double2hiint(v); }
-  static __device__ __forceinline__ int expo_of_hi(int h) { return ((h >> 20) & 0x7ff) - 1023; }
-  static __device__ __forceinline__ int clamp_shift(int s) { return s < -1000 ? -1000 : (s > 1000 ? 1000 : s); }
-  static __device__ __forceinline__ double pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }
-};
-template <>
-struct Fp<float> {
-  static constexpr int WINDOW = 32;
-  static __device__ __forceinline__ int hi(float v) { return __float_as_int(v); }
-  static __device__ __forceinline__ int expo_of_hi(int h) { return ((h >> 23) & 0xff) - 127; }
-  static __device__ __forceinline__ int clamp_shift(int s) { return s < -120 ? -120 : (s > 120 ? 120 : s); }
-  static __device__ __forceinline__ float pow2(int e) { return __int_as_float((e + 127) << 23); }
-};
-// 2^e for any int e as a double (used for the per-frame posterior scale; may under/overflow)
+__device__ __forceinline__ int expo_hi(int h) { return ((h >> 20) & 0x7ff) - 1023; }
+// 2^e as double, e in [-1022, 1023]
+__device__ __forceinline__ double pow2d(int e) { return __hiloint2double((e + 1023) << 20, 0); }
+// 2^e, flushing to zero below the normal range; e <= 1023
+__device__ __forceinline__ double pow2_flush(int e) { return e < -1022 ? 0.0 : pow2d(e); }
+// 2^e for any int e (gradual underflow, overflow to inf)
 __device__ __forceinline__ double pow2_wide(int e) {
   if (e < -1070) return 0.0;
   if (e > 1023) return INFINITY;
-  if (e >= -1022) return __hiloint2double((e + 1023) << 20, 0);
-  return __hiloint2double((e + 1023 + 60) << 20, 0) * __hiloint2double((1023 - 60) << 20, 0);
+  if (e >= -1022) return pow2d(e);
+  return pow2d(e + 60) * pow2d(-60);
+}
+// A double cut to its upper 32 bits (sign, 11-bit exponent, 20-bit mantissa, round to nearest):
+// the shared-memory format of the helper's sums -- full fp64 range at 4 bytes per cell.
+__device__ __forceinline__ int pack_hi(double v) { return __double2hiint(v) + (int)((unsigned)__double2loint(v) >> 31); }
+__device__ __forceinline__ double unpack_hi(int h) { return __hiloint2double(h, 0); }
+// exp(lp) as a double: fp32 mantissa (one ex2 on the fractional part) but the exponent goes straight
+// into the fp64 exponent field, so log-probs down to -700 stay non-zero (fp32 exp dies at -87)
+__device__ __forceinline__ double prob_of(float lp) {
+  const float t = lp * 1.4426950408889634f;
+  if (!(t > -1000.f)) return 0.0;  // also catches -inf and NaN
+  const float k = floorf(t);
+  const double m = (double)exp2f(t - k);  // [1,2]
+  return __hiloint2double(__double2hiint(m) + ((int)k << 20), __double2loint(m));
 }
 
 struct LossParams {
@@ -83,123 +88,202 @@ struct LossParams {
   float* grad;
   unsigned* counter;
   unsigned char* ckpt;  // per CTA: [2 dirs][nseg_max] strips + exponents
-  size_t ckpt_cta_bytes;
+  size_t ckpt_cta_bytes, ckpt_rec_bytes;
   int nseg_max;
   int K;       // frames per segment / pipeline stage
   int NCmax;   // cells per lane the shared-memory stages are sized for
-  int VP;      // p-row stride in elements (V + dummy zero column, even)
-  int Spad;    // staging capacity (labels)
+  int VP;      // p-row stride in doubles (V + dummy zero column, even)
+  int Spad;    // label staging capacity, multiple of 256
+  int GS;      // floats per staged frame: Spad label posteriors | 32 blank partials | flag
   int use_tma;
 };
 
-struct LossSmem {  // offsets into dynamic shared memory, identical on host and device
-  size_t stage_bytes, pR_off, wR_off, wE_off;  // within a stage
-  size_t stages_off, raw_off, raw_slot_bytes, gst_off, lab_off, pos_off, cls_off, bar_off, scal_off, total;
+struct LossSmem {  // byte offsets into dynamic shared memory, identical on host and device
+  size_t p_slot, w_slot, we_slot, g_slot, raw_slot;  // sizes
+  size_t p_off, w_off, we_off, g_off, raw_off;       // per half: ring bases (half stride = half_bytes)
+  size_t half_bytes, lab_off, pos_off, cls_off, bar_off, scal_off, total;
 };
 
-template <typename R>
-__host__ __device__ inline LossSmem loss_smem_layout(int K, int NCmax, int V, int VP, int Spad) {
+// mbarrier indices within a half
+constexpr int B_PFULL = 0, B_PEMPTY = LS_NP, B_WFULL = 2 * LS_NP, B_WEMPTY = 2 * LS_NP + 2, B_GFULL = 2 * LS_NP + 4,
+              B_GEMPTY = 2 * LS_NP + 6, B_HPFULL = 2 * LS_NP + 8, B_RAW = 3 * LS_NP + 8, B_PER_HALF = 3 * LS_NP + 8 + LS_NRAW;
+
+__host__ __device__ inline LossSmem loss_smem_layout(int K, int NCmax, int V, int VP, int GS, int S_tab) {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   LossSmem m;
-  m.pR_off = 0;
-  m.wR_off = al((size_t)K * VP * sizeof(R));
-  m.wE_off = m.wR_off + al((size_t)K * NCmax * 32 * sizeof(R));
-  m.stage_bytes = m.wE_off + al((size_t)K * 4);
+  m.p_slot = al((size_t)K * VP * 8);
+  m.w_slot = al((size_t)K * NCmax * 32 * 4);
+  m.we_slot = al((size_t)K * 32 * 4);
+  m.g_slot = al((size_t)K * GS * 4);
+  m.raw_slot = al((size_t)K * V * 4);
   size_t o = 0;
-  m.stages_off = o; o += 4 * m.stage_bytes;                     // [half][stage]
-  m.raw_slot_bytes = al((size_t)K * V * 4);
-  m.raw_off = o; o += 2 * LS_NRAW * m.raw_slot_bytes;           // [half][slot]
-  m.gst_off = o; o += 2 * al((size_t)Spad * 4);                 // [half]
-  m.lab_off = o; o += al((size_t)Spad * 4);
-  m.pos_off = o; o += al((size_t)Spad * 4);
+  m.p_off = o; o += LS_NP * m.p_slot;
+  m.w_off = o; o += 2 * m.w_slot;
+  m.we_off = o; o += 2 * m.we_slot;
+  m.g_off = o; o += 2 * m.g_slot;
+  m.raw_off = o; o += LS_NRAW * m.raw_slot;
+  m.half_bytes = o;
+  o = 2 * m.half_bytes;
+  m.lab_off = o; o += al((size_t)S_tab * 4);
+  m.pos_off = o; o += al((size_t)S_tab * 4);
   m.cls_off = o; o += al((size_t)(V + 2) * 4);
-  m.bar_off = o; o += al((size_t)(4 + 4 + 2 * LS_NRAW + 2) * 8);  // full[2][2] empty[2][2] raw[2][NRAW] p1done[2]
+  m.bar_off = o; o += al((size_t)(2 * B_PER_HALF + 2) * 8);
   m.scal_off = o; o += 64;
   m.total = o;
   return m;
 }
 
 struct LossScal {
-  int utt, b, T, S, bad, nc;
+  int utt, b, T, S, bad;
   float scale;
 };
 
-// ------------------------------------------------------------------ the recursion step
-// x: strip of NC cells (cell index = lane*NC + i, even i = blank).  On return w holds the
-// pre-emission sums and x the post-emission values of the new frame.
-template <typename R, int NC>
-__device__ __forceinline__ void ctc_step(R (&x)[NC], R (&w)[NC], const int (&lam)[NC / 2], unsigned skipm,
-                                         const R* __restrict__ prow, int blank) {
-  R up = __shfl_up_sync(FULL, x[NC - 1], 1);
-  if (lane_id() == 0) up = R(0);
-  const R pb = prow[blank];
-#pragma unroll
-  for (int i = NC - 1; i >= 0; --i) {
-    const R a1 = (i >= 1) ? x[i >= 1 ? i - 1 : 0] : up;
-    R s = x[i] + a1;
-    if (i & 1) {
-      const R a2 = (i >= 2) ? x[i >= 2 ? i - 2 : 0] : up;
-      if ((skipm >> (i >> 1)) & 1u) s += a2;
-      w[i] = s;
-      x[i] = s * prow[lam[i >> 1]];
+// ------------------------------------------------------------------ sweep state and steps
+// Strip of NC cells per lane (cell = lane*NC + i, even i = blank) with ONE exponent e per lane:
+// true value = x[i] * 2^e.  z: the whole strip is zero (its exponent is meaningless).
+// fin caches 2^(neighbour exponent - e), valid while ein_seen == the neighbour's exponent.
+template <int NC>
+struct Strip {
+  double x[NC];
+  double fin;
+  int e, ein_seen;
+  bool z;
+};
+
+// bring the neighbour's boundary values a, b (exponent ein) into my basis
+template <int NC>
+__device__ __forceinline__ void align_in(Strip<NC>& s, int ein, double& a, double& b) {
+  if (a != 0.0 || b != 0.0) {
+    if (s.z) {  // first mass reaches my strip: adopt the neighbour's basis
+      s.e = ein;
+      s.z = false;
+      s.fin = 1.0;
+      s.ein_seen = ein;
     } else {
-      w[i] = s;
-      x[i] = s * pb;
+      if (ein != s.ein_seen) {
+        int d = ein - s.e;
+        if (d > E_ADOPT) {  // neighbour dwarfs me: rebase my strip (rare, divergent)
+          const double f = pow2_wide(-d);
+#pragma unroll
+          for (int i = 0; i < NC; ++i) s.x[i] *= f;
+          s.e = ein;
+          d = 0;
+        }
+        s.fin = pow2_flush(d);
+        s.ein_seen = ein;
+      }
+      a *= s.fin;
+      b *= s.fin;
     }
   }
 }
 
-template <typename R, int NC>
-__device__ __forceinline__ void ctc_rescale(R (&x)[NC], int& E) {
-  int m = 0;
-#pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int h = Fp<R>::hi(x[i]);
-    m = h > m ? h : m;
+// DIR 0: cell c pulls from c-1 and (odd c, skip allowed) c-2.  DIR 1: from c+1 and c+2.
+// STORE (helper): also emit the pre-emission sums, packed to 32 bits.
+// prow: this frame's probabilities (dummy column = 0); lam: byte offsets of my label columns.
+template <int NC, int DIR, bool STORE>
+__device__ __forceinline__ void ctc_step(Strip<NC>& s, const int (&lam)[NC / 2], unsigned skipm, const unsigned char* __restrict__ prow,
+                                         int blank_off, int* __restrict__ wdst) {
+  double (&x)[NC] = s.x;
+  double n0, n1 = 0.0;
+  int ein;
+  if (DIR == 0) {
+    n0 = __shfl_up_sync(FULL, x[NC - 1], 1);
+    ein = __shfl_up_sync(FULL, s.e, 1);
+    if (lane_id() == 0) n0 = 0.0;
+  } else {
+    n0 = __shfl_down_sync(FULL, x[0], 1);
+    n1 = __shfl_down_sync(FULL, x[1], 1);
+    ein = __shfl_down_sync(FULL, s.e, 1);
+    if (lane_id() == 31) n0 = n1 = 0.0;
   }
-  m = __reduce_max_sync(FULL, m);
-  if (m == 0) return;
-  const int e = Fp<R>::expo_of_hi(m);
-  if (e > Fp<R>::WINDOW || e < -Fp<R>::WINDOW) {
-    const int sh = Fp<R>::clamp_shift(-e);
-    const R f = Fp<R>::pow2(sh);
+  align_in<NC>(s, ein, n0, n1);
+  const double pb = *reinterpret_cast<const double*>(prow + blank_off);
 #pragma unroll
-    for (int i = 0; i < NC; ++i) x[i] *= f;
-    E -= sh;
+  for (int ii = 0; ii < NC; ++ii) {
+    const int i = DIR == 0 ? NC - 1 - ii : ii;  // update order keeps the not-yet-read inputs intact
+    double a1, a2;
+    if (DIR == 0) {
+      a1 = (i >= 1) ? x[i >= 1 ? i - 1 : 0] : n0;
+      a2 = (i >= 2) ? x[i >= 2 ? i - 2 : 0] : n0;
+    } else {
+      a1 = (i + 1 < NC) ? x[i + 1 < NC ? i + 1 : 0] : n0;
+      a2 = (i + 2 < NC) ? x[i + 2 < NC ? i + 2 : 0] : n1;  // odd i = NC-1: next lane's cell 1
+    }
+    double sum = x[i] + a1;
+    if (i & 1) {
+      if ((skipm >> (i >> 1)) & 1u) sum += a2;
+      x[i] = sum * *reinterpret_cast<const double*>(prow + lam[i >> 1]);
+    } else {
+      x[i] = sum * pb;
+    }
+    if (STORE) wdst[i * 32] = pack_hi(sum);
   }
 }
 
-// per-lane label columns / skip mask for sweep direction dir (0 forward, 1 reversed labels)
+// renormalise my strip so that its largest cell is in [1,2); branch free
+template <int NC>
+__device__ __forceinline__ void renorm(Strip<NC>& s) {
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int h = __double2hiint(s.x[i]);
+    m = h > m ? h : m;
+  }
+  int ex = expo_hi(m);
+  ex = ex < -1022 ? -1022 : ex;
+  const bool zero = (m == 0);
+  const double f = zero ? 1.0 : pow2d(-ex);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s.x[i] *= f;
+  s.e += zero ? 0 : ex;
+  s.z = zero;
+  s.ein_seen = E_NONE;  // my basis moved: the cached incoming scale is stale
+}
+
+// start state of sweep dir: the virtual frame before the first one (one cell = 1)
+template <int NC>
+__device__ __forceinline__ void sweep_init(int dir, int L, Strip<NC>& s) {
+  const int lane = lane_id();
+  const int cell = dir ? L - 1 : 0;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s.x[i] = (lane * NC + i == cell) ? 1.0 : 0.0;
+  s.e = 0;
+  s.z = (lane != cell / NC);
+  s.fin = 1.0;
+  s.ein_seen = E_NONE;
+}
+
+// per-lane label column offsets (bytes into a p row) and skip mask for sweep direction dir
 template <int NC>
 __device__ __forceinline__ void lane_labels(int dir, int S, int V, const int* __restrict__ lab, int (&lam)[NC / 2], unsigned& skipm) {
   const int lane = lane_id();
   skipm = 0u;
 #pragma unroll
   for (int k = 0; k < NC / 2; ++k) {
-    const int jl = lane * (NC / 2) + k;  // local label index of odd cell 2k+1
-    int col = V;                         // dummy column (p = 0) beyond the target
-    if (jl < S) {
-      const int j = dir ? S - 1 - jl : jl;
+    const int j = lane * (NC / 2) + k;  // label index of odd cell 2k+1
+    int col = V;                        // dummy column (p = 0) beyond the target
+    if (j < S) {
       col = lab[j];
-      if (jl >= 1) {
-        const int jp = dir ? j + 1 : j - 1;
-        if (lab[jp] != col) skipm |= 1u << k;
-      }
+      const int jn = dir ? j + 1 : j - 1;  // the label two cells further along the pull direction
+      if (jn >= 0 && jn < S && lab[jn] != col) skipm |= 1u << k;
     }
-    lam[k] = col;
+    lam[k] = col * 8;
   }
 }
 
-struct Pipe {  // per half
-  unsigned char* stage[2];
-  uint64_t* full;   // [2]
-  uint64_t* empty;  // [2]
-  uint64_t* rawbar; // [NRAW]
-  float* raw;       // [NRAW][K*V]
-  size_t raw_slot_floats;
+struct Half {  // shared-memory views of one half's rings
+  unsigned char* base;
+  uint64_t* bar;
+  size_t p_off, p_slot, w_off, w_slot, we_off, we_slot, g_off, g_slot, raw_off, raw_slot;
+  __device__ __forceinline__ unsigned char* p(int slot) const { return base + p_off + slot * p_slot; }
+  __device__ __forceinline__ int* w(int slot) const { return reinterpret_cast<int*>(base + w_off + slot * w_slot); }
+  __device__ __forceinline__ int* we(int slot) const { return reinterpret_cast<int*>(base + we_off + slot * we_slot); }
+  __device__ __forceinline__ float* g(int slot) const { return reinterpret_cast<float*>(base + g_off + slot * g_slot); }
+  __device__ __forceinline__ float* raw(int slot) const { return reinterpret_cast<float*>(base + raw_off + slot * raw_slot); }
 };
 
-// production descriptor: which K-frame block of which sweep direction
+// which K-frame block of which sweep direction production q of half h refers to
 struct Prod {
   int dir, tau0, n;
 };
@@ -218,292 +302,320 @@ __device__ __forceinline__ Prod prod_desc(int q, int h, int m_h, int m_o, int K,
   return d;
 }
 
-// ------------------------------------------------------------------ helper warp
-template <typename R, int NC>
-__device__ void helper_role(const LossParams& P, const LossSmem& M, const Pipe& pipe, int h, int b, int Tb, int S, int m_h, int m_o,
-                            const int* __restrict__ lab, uint64_t* p1done_other, unsigned uiter, unsigned& qg,
-                            unsigned char* ckpt_cta) {
+struct Plan {  // per utterance, per half
+  int h, b, Tb, S, L, m_h, m_o, NP1, NSEG, NSEG_RUN, NPROD;
+};
+
+// ------------------------------------------------------------------ L: loader / converter
+__device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl, unsigned qbase, unsigned jbase) {
   const int lane = lane_id();
   const int K = P.K, V = P.V, VP = P.VP;
-  const int L = 2 * S + 1;
-  const int NP1 = (m_h + K - 1) / K, NSEG = (m_o + K - 1) / K, NPROD = NP1 + NSEG;
-  const int d = h ^ 1;  // direction this helper recomputes
-  const float* base = P.lp + (int64_t)b * P.sb;
-
-  int lam[NC / 2];
-  unsigned skipm;
-  lane_labels<NC>(d, S, V, lab, lam, skipm);
-  int woff[NC];  // where my cell's value goes in the main's (reversed) layout, -1 = nowhere
-#pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int sig_o = lane * NC + i;
-    int off = -1;
-    if (sig_o < L) {
-      const int sig = L - 1 - sig_o;
-      off = (sig % NC) * 32 + sig / NC;
-    }
-    woff[i] = off;
-  }
-
-  const unsigned rawbase = qg;
+  const float* base = P.lp + (int64_t)pl.b * P.sb;
   auto issue_raw = [&](int q) {  // lane 0
-    const Prod pd = prod_desc(q, h, m_h, m_o, K, NP1, NSEG);
-    const int t_lo = pd.dir ? Tb - pd.tau0 - pd.n : pd.tau0;
-    const unsigned rq = rawbase + (unsigned)q;
-    const int slot = (int)(rq % LS_NRAW);
+    const Prod pd = prod_desc(q, pl.h, pl.m_h, pl.m_o, K, pl.NP1, pl.NSEG);
+    const int t_lo = pd.dir ? pl.Tb - pd.tau0 - pd.n : pd.tau0;
+    const int slot = (int)((qbase + (unsigned)q) % LS_NRAW);
     const uint32_t bytes = (uint32_t)(pd.n * V * 4);
-    mbar_arrive_expect_tx(&pipe.rawbar[slot], bytes);
-    bulk_g2s(pipe.raw + slot * pipe.raw_slot_floats, base + (int64_t)t_lo * P.st, bytes, &pipe.rawbar[slot]);
+    mbar_arrive_expect_tx(&hf.bar[B_RAW + slot], bytes);
+    bulk_g2s(hf.raw(slot), base + (int64_t)t_lo * P.st, bytes, &hf.bar[B_RAW + slot]);
   };
   if (P.use_tma && lane == 0)
-    for (int q = 0; q < NPROD && q < LS_NRAW - 1; ++q) issue_raw(q);
-
-  R x[NC], w[NC];
-  for (int q = 0; q < NPROD; ++q) {
-    if (P.use_tma && lane == 0 && q + LS_NRAW - 1 < NPROD) issue_raw(q + LS_NRAW - 1);
-    const int s = (int)(qg & 1u);
-    mbar_wait(&pipe.empty[s], ((qg >> 1) & 1u) ^ 1u);
-    const Prod pd = prod_desc(q, h, m_h, m_o, K, NP1, NSEG);
-    R* pR = reinterpret_cast<R*>(pipe.stage[s] + M.pR_off);
-    // ---- rows: exp() into the stage, row r <-> local time tau0 + r of direction pd.dir
+    for (int q = 0; q < pl.NPROD && q < LS_NRAW - 1; ++q) issue_raw(q);
+  const int V4 = V >> 2;
+  for (int q = 0; q < pl.NPROD; ++q) {
+    // every lane has observed raw slot (q-1)'s completion before lane 0 re-arms that slot's mbarrier
+    __syncwarp();
+    if (P.use_tma && lane == 0 && q + LS_NRAW - 1 < pl.NPROD) issue_raw(q + LS_NRAW - 1);
+    const unsigned Q = qbase + (unsigned)q;
+    const int slot = (int)(Q % LS_NP);
+    mbar_wait(&hf.bar[B_PEMPTY + slot], ((Q / LS_NP) & 1u) ^ 1u);
+    const Prod pd = prod_desc(q, pl.h, pl.m_h, pl.m_o, K, pl.NP1, pl.NSEG);
+    double* pR = reinterpret_cast<double*>(hf.p(slot));
+    // row r of the slot <-> local time tau0 + r of direction pd.dir
     if (P.use_tma) {
-      const unsigned rq = rawbase + (unsigned)q;
-      const int slot = (int)(rq % LS_NRAW);
-      mbar_wait(&pipe.rawbar[slot], (rq / LS_NRAW) & 1u);
-      const float* raw = pipe.raw + slot * pipe.raw_slot_floats;
-      for (int idx = lane; idx < pd.n * V; idx += 32) {
-        const int r = idx / V, v = idx - r * V;
-        const int br = pd.dir ? pd.n - 1 - r : r;
-        pR[r * VP + v] = (R)expf(raw[br * V + v]);
+      const int rs = (int)(Q % LS_NRAW);
+      mbar_wait(&hf.bar[B_RAW + rs], (Q / LS_NRAW) & 1u);
+      const float4* raw4 = reinterpret_cast<const float4*>(hf.raw(rs));
+      for (int idx = lane; idx < pd.n * V4; idx += 32) {  // V % 4 == 0 on this path
+        const int br = idx / V4, c4 = idx - br * V4;
+        const int r = pd.dir ? pd.n - 1 - br : br;
+        const float4 v = raw4[idx];
+        double2* dst = reinterpret_cast<double2*>(pR + r * VP + 4 * c4);
+        dst[0] = make_double2(prob_of(v.x), prob_of(v.y));
+        dst[1] = make_double2(prob_of(v.z), prob_of(v.w));
       }
     } else {
-      const int t_lo = pd.dir ? Tb - pd.tau0 - pd.n : pd.tau0;
-      for (int idx = lane; idx < pd.n * V; idx += 32) {
-        const int r = idx / V, v = idx - r * V;
+      const int t_lo = pd.dir ? pl.Tb - pd.tau0 - pd.n : pd.tau0;
+      for (int r = 0; r < pd.n; ++r) {
         const int br = pd.dir ? pd.n - 1 - r : r;
-        pR[r * VP + v] = (R)expf(ld_stream(base + (int64_t)(t_lo + br) * P.st + v));
+        for (int v = lane; v < V; v += 32) pR[r * VP + v] = prob_of(ld_stream(base + (int64_t)(t_lo + br) * P.st + v));
       }
     }
-    if (lane < pd.n) pR[lane * VP + V] = R(0);  // dummy column (K <= 32)
-    __syncwarp();
-    // ---- phase 2: recompute segment of direction d from its checkpoint
-    if (q >= NP1) {
-      if (q == NP1) mbar_wait(p1done_other, uiter & 1u);  // the other main has published its checkpoints
-      const int seg = pd.tau0 / K;
-      int E = 0;
-      if (seg == 0) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) x[i] = R(0);
-        if (lane == 0) x[0] = R(1);
-      } else {
-        const unsigned char* cp = ckpt_cta + ((size_t)d * P.nseg_max + seg) * ((size_t)P.NCmax * 32 * sizeof(R) + 16);
-        const R* cx = reinterpret_cast<const R*>(cp);
-#pragma unroll
-        for (int i = 0; i < NC; ++i) x[i] = cx[i * 32 + lane];
-        E = *reinterpret_cast<const int*>(cp + (size_t)P.NCmax * 32 * sizeof(R));
-      }
-      R* wR = reinterpret_cast<R*>(pipe.stage[s] + M.wR_off);
-      int* wE = reinterpret_cast<int*>(pipe.stage[s] + M.wE_off);
-      int tau = pd.tau0;
-      for (int r = 0; r < pd.n; ++r, ++tau) {
-        const int Eb = E;
-        ctc_step<R, NC>(x, w, lam, skipm, pR + r * VP, P.blank);
-        R* dst = wR + (size_t)r * NC * 32;
-#pragma unroll
-        for (int i = 0; i < NC; ++i)
-          if (woff[i] >= 0) dst[woff[i]] = w[i];
-        if (lane == 0) wE[r] = Eb;
-        if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) ctc_rescale<R, NC>(x, E);
-      }
-    }
-    mbar_arrive(&pipe.full[s]);  // all 32 lanes: their shared-memory writes are ordered before it
-    ++qg;
+    if (lane < pd.n) pR[lane * VP + V] = 0.0;  // dummy column (K <= 32)
+    mbar_arrive(&hf.bar[B_PFULL + slot]);
+    if (q >= pl.NP1) mbar_arrive(&hf.bar[B_HPFULL + (int)((jbase + (unsigned)(q - pl.NP1)) % LS_NP)]);  // the helper's view
   }
 }
 
-// ------------------------------------------------------------------ main warp
-template <typename R, int NC>
-__device__ void main_role(const LossParams& P, const LossSmem& M, const Pipe& pipe, int h, int b, int Tb, int S, int m_h, int m_o,
-                          const int* __restrict__ lab, const int* __restrict__ pos, const int* __restrict__ cls, float* gst,
-                          uint64_t* p1done_mine, float scale, unsigned& qg, unsigned char* ckpt_cta) {
+// ------------------------------------------------------------------ H: recompute helper (phase 2 only)
+template <int NC, int DIR>
+__device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ lab, uint64_t* p1done_other,
+                            unsigned uiter, unsigned qbase, unsigned jbase, const unsigned char* ckpt_cta) {
   const int lane = lane_id();
-  const int K = P.K, V = P.V, VP = P.VP;
-  const int L = 2 * S + 1;
-  const int NP1 = (m_h + K - 1) / K, NSEG = (m_o + K - 1) / K;
+  const int K = P.K, VP8 = P.VP * 8, blank_off = P.blank * 8;
+  int lam[NC / 2];
+  unsigned skipm;
+  lane_labels<NC>(DIR, pl.S, P.V, lab, lam, skipm);
+  Strip<NC> s;
+  for (int j = 0; j < pl.NSEG_RUN; ++j) {
+    const unsigned Q = qbase + (unsigned)(pl.NP1 + j), J = jbase + (unsigned)j;
+    const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
+    if (j == 0) mbar_wait(p1done_other, uiter & 1u);  // the other main has published its checkpoints
+    // rows of production Q are ready.  A barrier of my own (armed for phase-2 productions only):
+    // I skip the phase-1 productions, so p_full's parity could alias by the time I get here.
+    mbar_wait(&hf.bar[B_HPFULL + (int)(J % LS_NP)], (J / LS_NP) & 1u);
+    mbar_wait(&hf.bar[B_WEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    const int seg = pl.NSEG - 1 - j;
+    const int tau0 = seg * K, n = min(K, pl.m_o - tau0);
+    if (seg == 0) {
+      sweep_init<NC>(DIR, pl.L, s);
+    } else {
+      const unsigned char* cp = ckpt_cta + ((size_t)DIR * P.nseg_max + seg) * P.ckpt_rec_bytes;
+      const double* cx = reinterpret_cast<const double*>(cp);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) s.x[i] = cx[i * 32 + lane];
+      const int* ce = reinterpret_cast<const int*>(cp + (size_t)P.NCmax * 32 * 8);
+      s.e = ce[lane];
+      s.z = ce[32 + lane] != 0;
+      s.fin = 1.0;
+      s.ein_seen = E_NONE;
+    }
+    const unsigned char* pR = hf.p(ps);
+    int* wR = hf.w(ws) + lane;
+    int* wE = hf.we(ws) + lane;
+    int tau = tau0;
+    for (int r = 0; r < n; ++r, ++tau) {
+      ctc_step<NC, DIR, true>(s, lam, skipm, pR + r * VP8, blank_off, wR + r * NC * 32);
+      wE[r * 32] = s.e;  // basis of the sums just stored (after alignment, before renorm)
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
+    }
+    mbar_arrive(&hf.bar[B_WFULL + ws]);
+  }
+}
 
+// ------------------------------------------------------------------ M: main sweep
+template <int NC, int DIR>
+__device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ lab, const int* __restrict__ pos,
+                          uint64_t* p1done_mine, unsigned qbase, unsigned jbase, unsigned char* ckpt_cta) {
+  const int lane = lane_id();
+  const int K = P.K, VP8 = P.VP * 8, blank_off = P.blank * 8;
   int lam[NC / 2], spos[NC / 2];
   unsigned skipm;
-  lane_labels<NC>(h, S, V, lab, lam, skipm);
+  lane_labels<NC>(DIR, pl.S, P.V, lab, lam, skipm);
 #pragma unroll
   for (int k = 0; k < NC / 2; ++k) {
-    const int jl = lane * (NC / 2) + k;
-    spos[k] = jl < S ? pos[h ? S - 1 - jl : jl] : -1;
+    const int j = lane * (NC / 2) + k;
+    spos[k] = j < pl.S ? pos[j] : -1;
   }
-  unsigned validm = 0u;  // cells of mine inside the lattice
-#pragma unroll
-  for (int i = 0; i < NC; ++i)
-    if (lane * NC + i < L) validm |= 1u << i;
-
-  R x[NC], w[NC];
-#pragma unroll
-  for (int i = 0; i < NC; ++i) x[i] = R(0);
-  if (lane == 0) x[0] = R(1);
-  int E = 0, tau = 0;
+  Strip<NC> s;
+  sweep_init<NC>(DIR, pl.L, s);
+  int tau = 0;
 
   // ---------------- phase 1: my half of the frames, checkpoint every K
-  for (int q = 0; q < NP1; ++q) {
-    const int s = (int)(qg & 1u);
-    mbar_wait(&pipe.full[s], (qg >> 1) & 1u);
-    const R* pR = reinterpret_cast<const R*>(pipe.stage[s] + M.pR_off);
-    const int n = min(K, m_h - q * K);
+  for (int q = 0; q < pl.NP1; ++q) {
+    const unsigned Q = qbase + (unsigned)q;
+    const int ps = (int)(Q % LS_NP);
+    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    const unsigned char* pR = hf.p(ps);
+    const int n = min(K, pl.m_h - q * K);
     for (int r = 0; r < n; ++r, ++tau) {
-      ctc_step<R, NC>(x, w, lam, skipm, pR + r * VP, P.blank);
-      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) ctc_rescale<R, NC>(x, E);
+      ctc_step<NC, DIR, false>(s, lam, skipm, pR + r * VP8, blank_off, nullptr);
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
     }
-    mbar_arrive(&pipe.empty[s]);
-    ++qg;
-    if (q + 1 < NP1) {  // state after frame (q+1)K-1 starts segment q+1
-      unsigned char* cp = ckpt_cta + ((size_t)h * P.nseg_max + (q + 1)) * ((size_t)P.NCmax * 32 * sizeof(R) + 16);
-      R* cx = reinterpret_cast<R*>(cp);
+    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    if (q + 1 < pl.NP1) {  // state after frame (q+1)K-1 starts segment q+1
+      unsigned char* cp = ckpt_cta + ((size_t)DIR * P.nseg_max + (q + 1)) * P.ckpt_rec_bytes;
+      double* cx = reinterpret_cast<double*>(cp);
 #pragma unroll
-      for (int i = 0; i < NC; ++i) cx[i * 32 + lane] = x[i];
-      if (lane == 0) *reinterpret_cast<int*>(cp + (size_t)P.NCmax * 32 * sizeof(R)) = E;
+      for (int i = 0; i < NC; ++i) cx[i * 32 + lane] = s.x[i];
+      int* ce = reinterpret_cast<int*>(cp + (size_t)P.NCmax * 32 * 8);
+      ce[lane] = s.e;
+      ce[32 + lane] = s.z ? 1 : 0;
     }
   }
   __threadfence_block();
   mbar_arrive(p1done_mine);
 
-  // ---------------- phase 2: the other half, with the other sweep's values from my helper
+  // ---------------- phase 2: the other half; posteriors = mine (post-emission) x other's (pre-emission)
   bool first = true, feasible = true;
   double invPm = 1.0;
   int eP = 0;
-  float* grow_base = P.grad ? P.grad + (int64_t)b * P.sb : nullptr;
-  for (int j = 0; j < NSEG; ++j) {
-    const int seg = NSEG - 1 - j;
-    const int n = min(K, m_o - seg * K);
-    const int s = (int)(qg & 1u);
-    mbar_wait(&pipe.full[s], (qg >> 1) & 1u);
-    const R* pR = reinterpret_cast<const R*>(pipe.stage[s] + M.pR_off);
-    const R* wR = reinterpret_cast<const R*>(pipe.stage[s] + M.wR_off);
-    const int* wE = reinterpret_cast<const int*>(pipe.stage[s] + M.wE_off);
+  const bool want_grad = P.grad != nullptr;
+  for (int j = 0; j < pl.NSEG_RUN; ++j) {
+    const unsigned Q = qbase + (unsigned)(pl.NP1 + j), J = jbase + (unsigned)j;
+    const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
+    const int seg = pl.NSEG - 1 - j;
+    const int n = min(K, pl.m_o - seg * K);
+    mbar_wait(&hf.bar[B_WFULL + ws], (J >> 1) & 1u);
+    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    if (want_grad) mbar_wait(&hf.bar[B_GEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    const unsigned char* pR = hf.p(ps);
+    const int* wR = hf.w(ws) + lane;
+    const int* wE = hf.we(ws) + lane;
+    float* gR = hf.g(ws);
     for (int r = n - 1; r >= 0; --r, ++tau) {
-      const R* prow = pR + r * VP;
-      ctc_step<R, NC>(x, w, lam, skipm, prow, P.blank);
-      // lattice occupancy: my post-emission value x other's pre-emission sum.  The two factors can
-      // each sit hundreds of binades below their sweep's maximum while their product is what
-      // matters, so the exponent k = E + Eo - eP is split over both operands before multiplying.
-      const R* wo = wR + (size_t)r * NC * 32 + lane;
-      const int Eo = wE[r];
+      ctc_step<NC, DIR, false>(s, lam, skipm, pR + r * VP8, blank_off, nullptr);
+      const int* wo = wR + r * NC * 32;
+      const int q_l = s.e + wE[r * 32];  // exponent of my lane's products
+      double g[NC];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) g[i] = s.x[i] * unpack_hi(wo[i * 32]);
       if (first) {
         first = false;
-        // largest product exponent over the lattice, and the x-exponent of a cell attaining it
-        int key = 0;
+        // P = sum over the lattice, combined across lanes at the largest lane exponent
+        double sl = 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const double xv = (double)x[i], wv = ((validm >> i) & 1u) ? (double)wo[i * 32] : 0.0;
-          if (xv > 0.0 && wv > 0.0) {
-            const int ex = Fp<double>::expo_of_hi(__double2hiint(xv)), ew = Fp<double>::expo_of_hi(__double2hiint(wv));
-            const int kk = ((ex + ew + 4096) << 12) | (ex + 2048);
-            key = kk > key ? kk : key;
-          }
-        }
-        key = __reduce_max_sync(FULL, key);
-        feasible = key != 0;
+        for (int i = 0; i < NC; ++i) sl += g[i];
+        const bool ok = sl > 0.0 && sl < INFINITY;
+        const int key = ok ? q_l + expo_hi(__double2hiint(sl)) : E_NONE;
+        const int Qm = __reduce_max_sync(FULL, key);
+        feasible = Qm > E_NONE;
         if (feasible) {
-          const int esum = (key >> 12) - 4096, ex = (key & 0xfff) - 2048;
-          const double fa = pow2_wide(-ex), fb = pow2_wide(-(esum - ex));
-          double ps = 0.0;
+          double tot = ok ? sl * pow2_wide(q_l - Qm) : 0.0;
 #pragma unroll
-          for (int i = 0; i < NC; ++i)
-            if ((validm >> i) & 1u) ps += ((double)x[i] * fa) * ((double)wo[i * 32] * fb);
-#pragma unroll
-          for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(FULL, ps, o);
-          const int e2 = Fp<double>::expo_of_hi(__double2hiint(ps));
-          const double pm = ps * pow2_wide(-e2);  // in [1,2)
+          for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+          const int et = expo_hi(__double2hiint(tot));
+          const double pm = tot * pow2_wide(-et);  // in [1,2)
           invPm = 1.0 / pm;
-          eP = e2 + esum + E + Eo;
-          if (h == 0 && lane == 0) P.nll[b] = (float)(-(log(pm) + (double)eP * 0.69314718055994530942));
-        } else if (h == 0 && lane == 0) {
-          P.nll[b] = P.zero_inf ? 0.f : INFINITY;
+          eP = Qm + et;
+          if (DIR == 0 && lane == 0) P.nll[pl.b] = (float)(-(log(pm) + (double)eP * 0.69314718055994530942));
+        } else if (DIR == 0 && lane == 0) {
+          P.nll[pl.b] = P.zero_inf ? 0.f : INFINITY;
         }
+        if (!want_grad) break;
       }
-      if (grow_base && feasible) {
-        int k = E + Eo - eP;
-        k = k < -2000 ? -2000 : (k > 2000 ? 2000 : k);
-        const int k1 = k / 2;
-        const double f1 = pow2_wide(k1) * invPm, f2 = pow2_wide(k - k1);
+      // stage this frame for G: label posteriors in class-sorted order + my lane's blank partial
+      float* gf = gR + (size_t)r * P.GS;
+      int kq = q_l - eP;
+      kq = kq > 1000 ? 1000 : kq;
+      const double c = feasible ? pow2_flush(kq) * invPm : 0.0;
+      double gb = 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-          w[i] = ((validm >> i) & 1u) ? (R)(((double)x[i] * f1) * ((double)wo[i * 32] * f2)) : R(0);
-      }
-      if (grow_base) {
-        const int t = h ? Tb - 1 - tau : tau;
-        float* grow = grow_base + (int64_t)t * P.st;
-        if (feasible) {
-          // blank class: even cells (w now holds normalised posteriors)
-          double gb = 0.0;
+      for (int i = 0; i < NC; i += 2) gb += g[i];
+      gf[P.Spad + lane] = (float)(gb * c);
 #pragma unroll
-          for (int i = 0; i < NC; i += 2) gb += (double)w[i];
-          float gbf = (float)gb;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) gbf += __shfl_xor_sync(FULL, gbf, o);
-          // label classes: stage posteriors in label-sorted order, then each lane sums its classes
-#pragma unroll
-          for (int k = 0; k < NC / 2; ++k)
-            if (spos[k] >= 0) gst[spos[k]] = (float)w[2 * k + 1];
-          __syncwarp();
-          for (int v = lane; v < V; v += 32) {
-            float g = 0.f;
-            if (v == P.blank) {
-              g = gbf;
-            } else {
-              const int a = cls[v], e = cls[v + 1];
-              for (int z = a; z < e; ++z) g += gst[z];
-            }
-            st_stream(grow + v, ((float)prow[v] - g) * scale);
-          }
-          __syncwarp();
-        } else {
-          const float fill = P.zero_inf ? 0.f : NAN;
-          for (int v = lane; v < V; v += 32) st_stream(grow + v, fill);
-        }
-      }
-      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) ctc_rescale<R, NC>(x, E);
+      for (int k = 0; k < NC / 2; ++k)
+        if (spos[k] >= 0) gf[spos[k]] = (float)(g[2 * k + 1] * c);
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
     }
-    mbar_arrive(&pipe.empty[s]);
-    ++qg;
+    if (want_grad) {
+      if (lane == 0) gR[P.Spad + 32] = feasible ? 1.f : 0.f;  // segment flag (frame 0's spare float)
+      mbar_arrive(&hf.bar[B_GFULL + ws]);
+    }
+    mbar_arrive(&hf.bar[B_WEMPTY + ws]);
+    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+  }
+}
+
+// ------------------------------------------------------------------ G: gradient writer
+// Takes part in every production's release (p_empty) so that the loader can never lap it.
+__device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ cls, float scale, unsigned qbase,
+                          unsigned jbase) {
+  const int lane = lane_id();
+  const int K = P.K, V = P.V, S = pl.S, h = pl.h, VP = P.VP;
+  float* grow_base = P.grad + (int64_t)pl.b * P.sb;
+  for (int q = 0; q < pl.NP1; ++q) {  // phase 1: nothing to write yet, just keep in step
+    const unsigned Q = qbase + (unsigned)q;
+    const int ps = (int)(Q % LS_NP);
+    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+  }
+  int tau = pl.m_h;
+  for (int j = 0; j < pl.NSEG_RUN; ++j) {
+    const unsigned Q = qbase + (unsigned)(pl.NP1 + j), J = jbase + (unsigned)j;
+    const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
+    const int seg = pl.NSEG - 1 - j;
+    const int n = min(K, pl.m_o - seg * K);
+    mbar_wait(&hf.bar[B_GFULL + ws], (J >> 1) & 1u);  // implies the rows of production Q are in place
+    float* gR = hf.g(ws);
+    const double* pR = reinterpret_cast<const double*>(hf.p(ps));
+    const bool feasible = gR[P.Spad + 32] != 0.f;
+    for (int r = n - 1; r >= 0; --r, ++tau) {
+      float* gf = gR + (size_t)r * P.GS;
+      const int t = h ? pl.Tb - 1 - tau : tau;
+      float* grow = grow_base + (int64_t)t * P.st;
+      if (feasible) {
+        float gb = gf[P.Spad + lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(FULL, gb, o);
+        // inclusive prefix sum over the class-sorted label posteriors, in place, 256 per pass
+        float carry = 0.f;
+        for (int base = 0; base < S; base += 256) {
+          float4* p4 = reinterpret_cast<float4*>(gf + base + lane * 8);
+          float4 a = p4[0], b = p4[1];
+          const int i0 = base + lane * 8;
+          a.x = i0 + 0 < S ? a.x : 0.f; a.y = i0 + 1 < S ? a.y : 0.f; a.z = i0 + 2 < S ? a.z : 0.f; a.w = i0 + 3 < S ? a.w : 0.f;
+          b.x = i0 + 4 < S ? b.x : 0.f; b.y = i0 + 5 < S ? b.y : 0.f; b.z = i0 + 6 < S ? b.z : 0.f; b.w = i0 + 7 < S ? b.w : 0.f;
+          a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
+          float incl = b.w;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+          }
+          const float off = carry + incl - b.w;  // everything before my 8
+          a.x += off; a.y += off; a.z += off; a.w += off; b.x += off; b.y += off; b.z += off; b.w += off;
+          p4[0] = a;
+          p4[1] = b;
+          carry += __shfl_sync(FULL, incl, 31);
+        }
+        __syncwarp();
+        for (int v = lane; v < V; v += 32) {
+          const int a = cls[v], b = cls[v + 1];
+          float gv = b > a ? gf[b - 1] - (a > 0 ? gf[a - 1] : 0.f) : 0.f;
+          if (v == P.blank) gv += gb;
+          st_stream(grow + v, ((float)pR[r * VP + v] - gv) * scale);
+        }
+        __syncwarp();
+      } else {
+        const float fill = P.zero_inf ? 0.f : NAN;
+        for (int v = lane; v < V; v += 32) st_stream(grow + v, fill);
+      }
+    }
+    mbar_arrive(&hf.bar[B_GEMPTY + ws]);
+    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
   }
 }
 
 // ------------------------------------------------------------------ kernel
-template <typename R>
-__global__ void __launch_bounds__(LS_THREADS, 1) loss_kernel(const LossParams P) {
+template <int NCMAX, int MINB>
+__global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams P) {
   SSD_DYN_SMEM(smem);
-  const LossSmem M = loss_smem_layout<R>(P.K, P.NCmax, P.V, P.VP, P.Spad);
+  const LossSmem M = loss_smem_layout(P.K, P.NCmax, P.V, P.VP, P.GS, P.S_max + 4);
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int h = warp & 1;
-  const bool helper = warp >= 2;
+  const int h = warp & 1, role = warp >> 1;  // 0 M, 1 H, 2 L, 3 G
 
   int* lab = reinterpret_cast<int*>(smem + M.lab_off);
   int* pos = reinterpret_cast<int*>(smem + M.pos_off);
   int* cls = reinterpret_cast<int*>(smem + M.cls_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M.bar_off);
   LossScal* sc = reinterpret_cast<LossScal*>(smem + M.scal_off);
-  uint64_t* p1done = bars + 8 + 2 * LS_NRAW;
+  uint64_t* p1done = bars + 2 * B_PER_HALF;
 
-  Pipe pipe;
-  pipe.stage[0] = smem + M.stages_off + (size_t)(2 * h + 0) * M.stage_bytes;
-  pipe.stage[1] = smem + M.stages_off + (size_t)(2 * h + 1) * M.stage_bytes;
-  pipe.full = bars + 2 * h;
-  pipe.empty = bars + 4 + 2 * h;
-  pipe.rawbar = bars + 8 + LS_NRAW * h;
-  pipe.raw_slot_floats = M.raw_slot_bytes / 4;
-  pipe.raw = reinterpret_cast<float*>(smem + M.raw_off) + (size_t)h * LS_NRAW * pipe.raw_slot_floats;
-  float* gst = reinterpret_cast<float*>(smem + M.gst_off) + (size_t)h * (((size_t)P.Spad * 4 + 15) / 16 * 4);
+  Half hf;
+  hf.base = smem + (size_t)h * M.half_bytes;
+  hf.bar = bars + h * B_PER_HALF;
+  hf.p_off = M.p_off; hf.p_slot = M.p_slot; hf.w_off = M.w_off; hf.w_slot = M.w_slot; hf.we_off = M.we_off; hf.we_slot = M.we_slot;
+  hf.g_off = M.g_off; hf.g_slot = M.g_slot; hf.raw_off = M.raw_off; hf.raw_slot = M.raw_slot;
 
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 32);               // full / empty: one arrival per lane
-    for (int i = 0; i < 2 * LS_NRAW; ++i) mbar_init(&bars[8 + i], 1);  // raw: lane 0 + tx bytes
+    for (int hh = 0; hh < 2; ++hh) {
+      uint64_t* b = bars + hh * B_PER_HALF;
+      for (int i = 0; i < B_RAW; ++i) mbar_init(&b[i], 32);  // one arrival per lane of the arriving warp
+      if (P.grad)
+        for (int i = 0; i < LS_NP; ++i) mbar_init(&b[B_PEMPTY + i], 64);  // rows are released by M and G
+      for (int i = 0; i < LS_NRAW; ++i) mbar_init(&b[B_RAW + i], 1);  // lane 0 + tx bytes
+    }
     mbar_init(&p1done[0], 32);
     mbar_init(&p1done[1], 32);
     mbar_fence_init();
@@ -511,8 +623,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) loss_kernel(const LossParams P)
   __syncthreads();
 
   unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
-  unsigned qg = 0u;  // productions so far on my half's pipeline (same value in main and helper)
-  unsigned uiter = 0u;
+  unsigned qbase = 0u, jbase = 0u, uiter = 0u;
 
   for (;; ++uiter) {
     // ---------------- next utterance + its label tables
@@ -521,7 +632,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) loss_kernel(const LossParams P)
       sc->utt = u;
       if (u < P.B) {
         const int b = P.order ? P.order[u] : u;
-        int64_t tl = P.in_len[b], sl = P.tg_len[b];
+        const int64_t tl = P.in_len[b], sl = P.tg_len[b];
         sc->b = b;
         sc->bad = (tl < 0 || tl > P.T || sl < 0 || sl > P.S_max) ? 1 : 0;
         sc->T = (int)(tl < 0 ? 0 : (tl > P.T ? P.T : tl));
@@ -567,49 +678,60 @@ __global__ void __launch_bounds__(LS_THREADS, 1) loss_kernel(const LossParams P)
     if (P.grad) {
       float* g0 = P.grad + (int64_t)b * P.sb;
       const float fill = bad ? NAN : 0.f;
-      const int64_t n = (int64_t)(P.T - Tb) * P.V;
-      for (int64_t i = tid; i < n; i += LS_THREADS) {
-        const int64_t r = i / P.V, v = i - r * P.V;
-        st_stream(g0 + (Tb + r) * P.st + v, fill);
-      }
+      for (int64_t r = Tb + warp; r < P.T; r += LS_THREADS / 32)
+        for (int v = lane; v < P.V; v += 32) st_stream(g0 + r * P.st + v, fill);
     }
     if (Tb == 0 && tid == 0) P.nll[b] = bad ? NAN : (S == 0 ? 0.f : (P.zero_inf ? 0.f : INFINITY));
 
+    Plan pl;
+    pl.h = h; pl.b = b; pl.Tb = Tb; pl.S = S; pl.L = 2 * S + 1;
     const int m = Tb / 2;
-    const int m_h = h == 0 ? m : Tb - m;
-    const int m_o = Tb - m_h;
-    const int nc_need = (2 * S + 1 + 31) / 32;
-#define SSD_ROLE(NCV)                                                                                                          \
-  do {                                                                                                                         \
-    if (helper)                                                                                                                \
-      helper_role<R, NCV>(P, M, pipe, h, b, Tb, S, m_h, m_o, lab, &p1done[h ^ 1], uiter, qg, ckpt_cta);                         \
-    else                                                                                                                       \
-      main_role<R, NCV>(P, M, pipe, h, b, Tb, S, m_h, m_o, lab, pos, cls, gst, &p1done[h], scale, qg, ckpt_cta);                \
+    pl.m_h = h == 0 ? m : Tb - m;
+    pl.m_o = Tb - pl.m_h;
+    pl.NP1 = (pl.m_h + P.K - 1) / P.K;
+    pl.NSEG = (pl.m_o + P.K - 1) / P.K;
+    // forward only: just the first phase-2 frame of the forward half is needed (it yields P)
+    pl.NSEG_RUN = P.grad ? pl.NSEG : (h == 0 ? min(pl.NSEG, 1) : 0);
+    pl.NPROD = pl.NP1 + pl.NSEG_RUN;
+    const int nc_need = (pl.L + 31) / 32;
+
+    if (role == 2) {
+      loader_role(P, hf, pl, qbase, jbase);
+    } else if (role == 3) {
+      if (P.grad) grad_role(P, hf, pl, cls, scale, qbase, jbase);
+    } else {
+      // main of half h sweeps direction h; its helper re-computes direction h^1
+#define SSD_ROLE(NCV)                                                                                              \
+  do {                                                                                                             \
+    if (role == 1) {                                                                                               \
+      if (h == 0) helper_role<NCV, 1>(P, hf, pl, lab, &p1done[1], uiter, qbase, jbase, ckpt_cta);                   \
+      else helper_role<NCV, 0>(P, hf, pl, lab, &p1done[0], uiter, qbase, jbase, ckpt_cta);                          \
+    } else {                                                                                                       \
+      if (h == 0) main_role<NCV, 0>(P, hf, pl, lab, pos, &p1done[0], qbase, jbase, ckpt_cta);                       \
+      else main_role<NCV, 1>(P, hf, pl, lab, pos, &p1done[1], qbase, jbase, ckpt_cta);                              \
+    }                                                                                                              \
   } while (0)
-    if (nc_need <= 2) SSD_ROLE(2);
-    else if (nc_need <= 4) SSD_ROLE(4);
-    else if (nc_need <= 8) SSD_ROLE(8);
-    else if (nc_need <= 14) SSD_ROLE(14);
-    else if (nc_need <= 20) SSD_ROLE(20);
-    else SSD_ROLE(32);
+      if constexpr (NCMAX <= 14) {
+        if (nc_need <= 4) SSD_ROLE(4);
+        else if (nc_need <= 8) SSD_ROLE(8);
+        else SSD_ROLE(14);
+      } else {
+        if (nc_need <= 20) SSD_ROLE(20);
+        else SSD_ROLE(32);
+      }
 #undef SSD_ROLE
-    __syncthreads();  // label tables and staging are reused by the next utterance
+    }
+    qbase += (unsigned)pl.NPROD;
+    jbase += (unsigned)pl.NSEG_RUN;
+    __syncthreads();  // label tables are rebuilt for the next utterance
   }
 }
 
 // ------------------------------------------------------------------ host side
 struct LossPlan {
-  int K, NCmax, VP, Spad, ctas_per_sm, grid, nseg_max;
-  size_t smem, ckpt_cta_bytes, ws_bytes;
-  bool use_float;
+  int K, NCmax, VP, Spad, GS, ctas_per_sm, grid, nseg_max;
+  size_t smem, ckpt_cta_bytes, ckpt_rec_bytes, ws_bytes;
 };
-
-static int nc_bucket(int need) {
-  const int b[6] = {2, 4, 8, 14, 20, 32};
-  for (int i = 0; i < 6; ++i)
-    if (need <= b[i]) return b[i];
-  return -1;
-}
 
 static int env_int(const char* name, int dflt) {
   const char* s = std::getenv(name);
@@ -627,28 +749,31 @@ static int device_sms() {
 #endif
 }
 
-template <typename R>
 static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& pl) {
-  pl.NCmax = nc_bucket((int)((2 * S_max + 1 + 31) / 32));
-  if (pl.NCmax < 0) return false;
+  const int need = (int)((2 * S_max + 1 + 31) / 32);
+  if (need > 32) return false;
+  pl.NCmax = need <= 14 ? 14 : 32;
   pl.VP = (int)((V + 2) & ~1LL);
-  pl.Spad = (int)((S_max + 3) / 4 * 4 + 4);
+  pl.Spad = (int)((S_max + 255) / 256 * 256);
+  if (pl.Spad == 0) pl.Spad = 256;
+  pl.GS = pl.Spad + 32 + 4;
   const size_t cap = 227 * 1024;
-  auto bytes = [&](int K) { return loss_smem_layout<R>(K, pl.NCmax, (int)V, pl.VP, pl.Spad).total; };
+  auto bytes = [&](int K) { return loss_smem_layout(K, pl.NCmax, (int)V, pl.VP, pl.GS, (int)S_max + 4).total; };
   const int kforce = env_int("SSD_LOSS_K", 0);
   int ctas = env_int("SSD_LOSS_CTAS", 0);
+  const int max_ctas = pl.NCmax <= 14 ? 2 : 1;  // register budget of the two kernel variants
   int K = 0;
   if (kforce > 0) {
     K = kforce > 32 ? 32 : kforce;
     if (bytes(K) > cap) return false;
     if (ctas <= 0) ctas = (int)(cap / (bytes(K) + 1024));
   } else {
-    // prefer two resident CTAs per SM (8 busy warps) when that still allows K >= 6
-    const int want = ctas > 0 ? ctas : 2;
-    for (int c = want; c >= 1 && K == 0; --c) {
+    // prefer two resident CTAs per SM (16 warps) when that still allows K >= 4
+    const int want = ctas > 0 ? ctas : max_ctas;
+    for (int c = want < max_ctas ? want : max_ctas; c >= 1 && K == 0; --c) {
       int k = 16;
       while (k >= 2 && (bytes(k) + 1024) * c > cap) --k;
-      if (k >= (c > 1 ? 6 : 2)) {
+      if (k >= (c > 1 ? 4 : 2)) {
         K = k;
         ctas = c;
       }
@@ -656,36 +781,36 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
     if (K == 0) return false;
   }
   if (ctas < 1) ctas = 1;
+  if (ctas > max_ctas) ctas = max_ctas;
   pl.K = K;
   pl.ctas_per_sm = ctas;
   pl.smem = bytes(K);
   const int64_t slots = (int64_t)device_sms() * ctas;
   pl.grid = (int)(B < slots ? B : slots);
   pl.nseg_max = (int)((T / 2 + 1 + K - 1) / K + 2);
-  pl.ckpt_cta_bytes = (size_t)2 * pl.nseg_max * ((size_t)pl.NCmax * 32 * sizeof(R) + 16);
+  pl.ckpt_rec_bytes = (size_t)pl.NCmax * 32 * 8 + 256;
+  pl.ckpt_cta_bytes = (size_t)2 * pl.nseg_max * pl.ckpt_rec_bytes;
   pl.ws_bytes = 256 + (size_t)pl.grid * pl.ckpt_cta_bytes;
   return true;
 }
 
-static bool loss_use_float() { return env_int("SSD_LOSS_FP32", 0) != 0; }
-
 size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
   LossPlan pl;
-  const bool ok = loss_use_float() ? plan_for<float>(B, T, V, S_max, pl) : plan_for<double>(B, T, V, S_max, pl);
-  return ok ? pl.ws_bytes : 256;
+  return plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 256;
 }
 
-template <typename R>
+template <int NCMAX, int MINB>
 static int loss_launch_t(LossParams& P, const LossPlan& pl, cudaStream_t stream) {
+  auto kfn = loss_kernel<NCMAX, MINB>;
 #ifndef SSD_EMU
-  cudaError_t e = cudaFuncSetAttribute(loss_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
   e = cudaMemsetAsync(P.counter, 0, 256, stream);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss: cudaMemsetAsync: %s", cudaGetErrorString(e));
 #else
   *P.counter = 0u;
 #endif
-  SSD_LAUNCH(loss_kernel<R>, (unsigned)pl.grid, LS_THREADS, pl.smem, stream, P);
+  SSD_LAUNCH(kfn, (unsigned)pl.grid, LS_THREADS, pl.smem, stream, P);
   return check_launch("loss_kernel");
 }
 
@@ -694,10 +819,9 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
                 int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
                 size_t ws_bytes, cudaStream_t stream) {
   if (B == 0) return SSD_OK;
-  const bool f32 = loss_use_float();
   LossPlan pl;
-  const bool ok = f32 ? plan_for<float>(B, T, V, S_max, pl) : plan_for<double>(B, T, V, S_max, pl);
-  if (!ok) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_loss: no shared-memory plan for V=%lld S_max=%lld", (long long)V, (long long)S_max);
+  if (!plan_for(B, T, V, S_max, pl))
+    return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_loss: no shared-memory plan for V=%lld S_max=%lld", (long long)V, (long long)S_max);
   if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
   LossParams P;
   P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
@@ -707,10 +831,10 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   P.nll = nll; P.grad = grad;
   P.counter = reinterpret_cast<unsigned*>(ws);
   P.ckpt = reinterpret_cast<unsigned char*>(ws) + 256;
-  P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.nseg_max = pl.nseg_max;
-  P.K = pl.K; P.NCmax = pl.NCmax; P.VP = pl.VP; P.Spad = pl.Spad;
+  P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nseg_max = pl.nseg_max;
+  P.K = pl.K; P.NCmax = pl.NCmax; P.VP = pl.VP; P.Spad = pl.Spad; P.GS = pl.GS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
-  return f32 ? loss_launch_t<float>(P, pl, stream) : loss_launch_t<double>(P, pl, stream);
+  return pl.NCmax <= 14 ? loss_launch_t<14, 2>(P, pl, stream) : loss_launch_t<32, 1>(P, pl, stream);
 }
 
 }  // namespace ssd

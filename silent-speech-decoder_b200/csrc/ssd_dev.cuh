@@ -82,9 +82,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 #else
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
+      // hint expires, instead of coming back to the issue slot every few hundred cycles
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 #endif

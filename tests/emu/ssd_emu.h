@@ -45,6 +45,8 @@ struct Fiber {
   int linear = 0;
   bool done = false;
   std::function<bool()> ready;  // empty => runnable
+  const char* wait_what = "";
+  const void* wait_obj = nullptr;
 };
 
 struct NamedBar {
@@ -106,13 +108,16 @@ inline void fiber_entry() {
   swapcontext(&s.cur->ctx, &s.sched);
 }
 
-inline void yield_until(std::function<bool()> cond) {
+inline void yield_until(std::function<bool()> cond, const char* what = "", const void* obj = nullptr) {
   State& s = S();
   if (cond()) return;
   s.cur->ready = std::move(cond);
+  s.cur->wait_what = what;
+  s.cur->wait_obj = obj;
   swapcontext(&s.cur->ctx, &s.sched);
 }
 
+inline unsigned char* dyn_smem();
 inline void flush_copies() {
   State& s = S();
   if (s.copies.empty()) return;
@@ -187,8 +192,16 @@ inline void run_block() {
     }
     if (!progress) {
       std::fprintf(stderr, "[ssd_emu] deadlock in block (%u,%u,%u): %d threads blocked\n", s.bidx.x, s.bidx.y, s.bidx.z, remaining);
-      for (int i = 0; i < n; ++i)
-        if (!s.fibers[i].done) { std::fprintf(stderr, "  first blocked thread: %d\n", i); break; }
+      for (int w0 = 0; w0 < n; w0 += 32) {
+        std::fprintf(stderr, "  warp %d:", w0 / 32);
+        for (int i = w0; i < w0 + 32 && i < n; ++i) {
+          if (s.fibers[i].done) { std::fprintf(stderr, " done"); continue; }
+          long off = (long)((const unsigned char*)s.fibers[i].wait_obj - dyn_smem());
+          if (i == w0 || s.fibers[i].wait_obj != s.fibers[i - 1].wait_obj || s.fibers[i].wait_what != s.fibers[i - 1].wait_what)
+            std::fprintf(stderr, " [lane %d..] %s @%ld", i - w0, s.fibers[i].wait_what, off);
+        }
+        std::fprintf(stderr, "\n");
+      }
       std::abort();
     }
   }
@@ -236,7 +249,7 @@ inline void bar_sync(int id, int count) {
   }
   const uint64_t g = b.gen;
   NamedBar* bp = &b;
-  yield_until([bp, g] { return bp->gen != g; });
+  yield_until([bp, g] { return bp->gen != g; }, "bar.sync", bp);
 }
 
 inline int lane_id() { return S().cur->linear & 31; }
@@ -267,7 +280,7 @@ inline const uint64_t* warp_exchange(unsigned mask, uint64_t mine) {
     ++w.gen;
   } else {
     WarpSlot* wp = &w;
-    yield_until([wp, g] { return wp->gen != g; });
+    yield_until([wp, g] { return wp->gen != g; }, "warp collective", wp);
   }
   return buf;
 }
@@ -308,7 +321,7 @@ inline bool mbar_test(void* p, unsigned parity) { return mbar_get(p).phase != (p
 inline void mbar_wait(void* p, unsigned parity) {
   MBar* m = &mbar_get(p);
   parity &= 1u;
-  yield_until([m, parity] { return m->phase != parity; });
+  yield_until([m, parity] { return m->phase != parity; }, parity ? "mbarrier parity 1" : "mbarrier parity 0", p);
 }
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
   if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15)) die("bulk copy needs 16-byte aligned src/dst/size");
