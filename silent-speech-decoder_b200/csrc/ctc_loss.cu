@@ -40,7 +40,7 @@ namespace ssd {
 constexpr int LS_THREADS = 256;
 constexpr int LS_NRAW = 4;     // raw-row ring depth per half (TMA prefetch distance = 3 segments)
 constexpr int LS_NP = 4;       // probability-row ring depth per half
-constexpr int LS_RESCALE = 4;  // frames between strip renormalisations
+constexpr int LS_RESCALE = 8;  // frames between strip renormalisations
 constexpr int E_ADOPT = 200;   // incoming exponent this far above mine: rebase my strip instead
 constexpr int E_NONE = -(1 << 30);
 
@@ -140,65 +140,46 @@ struct LossScal {
 
 // ------------------------------------------------------------------ sweep state and steps
 // Strip of NC cells per lane (cell = lane*NC + i, even i = blank) with ONE exponent e per lane:
-// true value = x[i] * 2^e.  z: the whole strip is zero (its exponent is meaningless).
-// fin caches 2^(neighbour exponent - e), valid while ein_seen == the neighbour's exponent.
+// true value = x[i] * 2^e.  Exponents only move in renorm() + exchange(), every LS_RESCALE frames,
+// in lockstep for all lanes; in between, the neighbour's boundary values are brought into my basis
+// by the cached factor fin = 2^(neighbour e - my e).  z: my strip was all zero at the last renorm.
 template <int NC>
 struct Strip {
   double x[NC];
   double fin;
-  int e, ein_seen;
+  int e;
   bool z;
 };
 
-// bring the neighbour's boundary values a, b (exponent ein) into my basis
+// this frame's probabilities of my cells, fetched one frame ahead of their use
 template <int NC>
-__device__ __forceinline__ void align_in(Strip<NC>& s, int ein, double& a, double& b) {
-  if (a != 0.0 || b != 0.0) {
-    if (s.z) {  // first mass reaches my strip: adopt the neighbour's basis
-      s.e = ein;
-      s.z = false;
-      s.fin = 1.0;
-      s.ein_seen = ein;
-    } else {
-      if (ein != s.ein_seen) {
-        int d = ein - s.e;
-        if (d > E_ADOPT) {  // neighbour dwarfs me: rebase my strip (rare, divergent)
-          const double f = pow2_wide(-d);
+struct PRow {
+  double lab[NC / 2];
+  double blank;
+};
+template <int NC>
+__device__ __forceinline__ void load_prow(PRow<NC>& p, const unsigned char* __restrict__ prow, const int (&lam)[NC / 2], int blank_off) {
+  p.blank = *reinterpret_cast<const double*>(prow + blank_off);
 #pragma unroll
-          for (int i = 0; i < NC; ++i) s.x[i] *= f;
-          s.e = ein;
-          d = 0;
-        }
-        s.fin = pow2_flush(d);
-        s.ein_seen = ein;
-      }
-      a *= s.fin;
-      b *= s.fin;
-    }
-  }
+  for (int k = 0; k < NC / 2; ++k) p.lab[k] = *reinterpret_cast<const double*>(prow + lam[k]);
 }
 
 // DIR 0: cell c pulls from c-1 and (odd c, skip allowed) c-2.  DIR 1: from c+1 and c+2.
 // STORE (helper): also emit the pre-emission sums, packed to 32 bits.
-// prow: this frame's probabilities (dummy column = 0); lam: byte offsets of my label columns.
 template <int NC, int DIR, bool STORE>
-__device__ __forceinline__ void ctc_step(Strip<NC>& s, const int (&lam)[NC / 2], unsigned skipm, const unsigned char* __restrict__ prow,
-                                         int blank_off, int* __restrict__ wdst) {
+__device__ __forceinline__ void ctc_step(Strip<NC>& s, unsigned skipm, const PRow<NC>& p, int* __restrict__ wdst) {
   double (&x)[NC] = s.x;
   double n0, n1 = 0.0;
-  int ein;
   if (DIR == 0) {
     n0 = __shfl_up_sync(FULL, x[NC - 1], 1);
-    ein = __shfl_up_sync(FULL, s.e, 1);
     if (lane_id() == 0) n0 = 0.0;
   } else {
     n0 = __shfl_down_sync(FULL, x[0], 1);
     n1 = __shfl_down_sync(FULL, x[1], 1);
-    ein = __shfl_down_sync(FULL, s.e, 1);
     if (lane_id() == 31) n0 = n1 = 0.0;
+    n1 *= s.fin;
   }
-  align_in<NC>(s, ein, n0, n1);
-  const double pb = *reinterpret_cast<const double*>(prow + blank_off);
+  n0 *= s.fin;
 #pragma unroll
   for (int ii = 0; ii < NC; ++ii) {
     const int i = DIR == 0 ? NC - 1 - ii : ii;  // update order keeps the not-yet-read inputs intact
@@ -213,23 +194,25 @@ __device__ __forceinline__ void ctc_step(Strip<NC>& s, const int (&lam)[NC / 2],
     double sum = x[i] + a1;
     if (i & 1) {
       if ((skipm >> (i >> 1)) & 1u) sum += a2;
-      x[i] = sum * *reinterpret_cast<const double*>(prow + lam[i >> 1]);
+      x[i] = sum * p.lab[i >> 1];
     } else {
-      x[i] = sum * pb;
+      x[i] = sum * p.blank;
     }
     if (STORE) wdst[i * 32] = pack_hi(sum);
   }
 }
 
-// renormalise my strip so that its largest cell is in [1,2); branch free
+// renormalise my strip so that its largest cell is in [1,2); branch free, tree-shaped maximum
 template <int NC>
 __device__ __forceinline__ void renorm(Strip<NC>& s) {
-  int m = 0;
+  int hw[NC];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int h = __double2hiint(s.x[i]);
-    m = h > m ? h : m;
-  }
+  for (int i = 0; i < NC; ++i) hw[i] = __double2hiint(s.x[i]);
+#pragma unroll
+  for (int w = 1; w < NC; w <<= 1)
+#pragma unroll
+    for (int i = 0; i + w < NC; i += 2 * w) hw[i] = hw[i] > hw[i + w] ? hw[i] : hw[i + w];
+  const int m = hw[0];
   int ex = expo_hi(m);
   ex = ex < -1022 ? -1022 : ex;
   const bool zero = (m == 0);
@@ -238,7 +221,39 @@ __device__ __forceinline__ void renorm(Strip<NC>& s) {
   for (int i = 0; i < NC; ++i) s.x[i] *= f;
   s.e += zero ? 0 : ex;
   s.z = zero;
-  s.ein_seen = E_NONE;  // my basis moved: the cached incoming scale is stale
+}
+
+// after every renorm: learn the neighbour's exponent and cache the factor for its boundary values.
+// An empty strip takes the exponent of the nearest non-empty strip on the side it pulls from, so
+// that the first mass reaching it lands close to its basis.
+template <int NC, int DIR>
+__device__ __forceinline__ void exchange(Strip<NC>& s) {
+  const int lane = lane_id();
+  const unsigned live = __ballot_sync(FULL, !s.z);
+  int src;
+  if (DIR == 0) {
+    const unsigned below = live & ((1u << lane) - 1u);
+    src = below ? 31 - __clz((int)below) : lane;
+  } else {
+    const unsigned above = lane == 31 ? 0u : (live >> (lane + 1));
+    src = above ? lane + __ffs((int)above) : lane;
+  }
+  const int e_near = __shfl_sync(FULL, s.e, src);
+  if (s.z) s.e = e_near;
+  const int ein = DIR == 0 ? __shfl_up_sync(FULL, s.e, 1) : __shfl_down_sync(FULL, s.e, 1);
+  int d = ein - s.e;
+  if ((DIR == 0 && lane == 0) || (DIR == 1 && lane == 31)) d = 0;
+  // an empty neighbour's exponent says nothing about what will arrive: never rebase on it
+  const bool nb_live = DIR == 0 ? (lane > 0 && ((live >> (lane - 1)) & 1u)) : (lane < 31 && ((live >> (lane + 1)) & 1u));
+  if (!nb_live) d = d > 1000 ? 1000 : d;
+  if (d > E_ADOPT && nb_live) {  // neighbour dwarfs me: rebase my strip (rare, divergent)
+    const double f = pow2_wide(-d);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) s.x[i] *= f;
+    s.e = ein;
+    d = 0;
+  }
+  s.fin = pow2_flush(d);
 }
 
 // start state of sweep dir: the virtual frame before the first one (one cell = 1)
@@ -251,7 +266,6 @@ __device__ __forceinline__ void sweep_init(int dir, int L, Strip<NC>& s) {
   s.e = 0;
   s.z = (lane != cell / NC);
   s.fin = 1.0;
-  s.ein_seen = E_NONE;
 }
 
 // per-lane label column offsets (bytes into a p row) and skip mask for sweep direction dir
@@ -387,17 +401,22 @@ __device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl,
       const int* ce = reinterpret_cast<const int*>(cp + (size_t)P.NCmax * 32 * 8);
       s.e = ce[lane];
       s.z = ce[32 + lane] != 0;
-      s.fin = 1.0;
-      s.ein_seen = E_NONE;
+      s.fin = reinterpret_cast<const double*>(ce + 64)[lane];
     }
     const unsigned char* pR = hf.p(ps);
     int* wR = hf.w(ws) + lane;
     int* wE = hf.we(ws) + lane;
     int tau = tau0;
+    PRow<NC> pc;
+    load_prow<NC>(pc, pR, lam, blank_off);
     for (int r = 0; r < n; ++r, ++tau) {
-      ctc_step<NC, DIR, true>(s, lam, skipm, pR + r * VP8, blank_off, wR + r * NC * 32);
-      wE[r * 32] = s.e;  // basis of the sums just stored (after alignment, before renorm)
-      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
+      ctc_step<NC, DIR, true>(s, skipm, pc, wR + r * NC * 32);
+      if (r + 1 < n) load_prow<NC>(pc, pR + (r + 1) * VP8, lam, blank_off);  // next frame's, in flight during the rest
+      wE[r * 32] = s.e;  // basis of the sums just stored
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
+        renorm<NC>(s);
+        exchange<NC, DIR>(s);
+      }
     }
     mbar_arrive(&hf.bar[B_WFULL + ws]);
   }
@@ -428,9 +447,15 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
     const unsigned char* pR = hf.p(ps);
     const int n = min(K, pl.m_h - q * K);
+    PRow<NC> pc;
+    load_prow<NC>(pc, pR, lam, blank_off);
     for (int r = 0; r < n; ++r, ++tau) {
-      ctc_step<NC, DIR, false>(s, lam, skipm, pR + r * VP8, blank_off, nullptr);
-      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
+      ctc_step<NC, DIR, false>(s, skipm, pc, nullptr);
+      if (r + 1 < n) load_prow<NC>(pc, pR + (r + 1) * VP8, lam, blank_off);  // next frame's, in flight during the rest
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
+        renorm<NC>(s);
+        exchange<NC, DIR>(s);
+      }
     }
     mbar_arrive(&hf.bar[B_PEMPTY + ps]);
     if (q + 1 < pl.NP1) {  // state after frame (q+1)K-1 starts segment q+1
@@ -441,6 +466,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
       int* ce = reinterpret_cast<int*>(cp + (size_t)P.NCmax * 32 * 8);
       ce[lane] = s.e;
       ce[32 + lane] = s.z ? 1 : 0;
+      reinterpret_cast<double*>(ce + 64)[lane] = s.fin;
     }
   }
   __threadfence_block();
@@ -463,19 +489,24 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     const int* wR = hf.w(ws) + lane;
     const int* wE = hf.we(ws) + lane;
     float* gR = hf.g(ws);
+    PRow<NC> pc;
+    load_prow<NC>(pc, pR + (n - 1) * VP8, lam, blank_off);
     for (int r = n - 1; r >= 0; --r, ++tau) {
-      ctc_step<NC, DIR, false>(s, lam, skipm, pR + r * VP8, blank_off, nullptr);
+      // the other sweep's sums for my cells (issued before the step so their latency is covered)
       const int* wo = wR + r * NC * 32;
-      const int q_l = s.e + wE[r * 32];  // exponent of my lane's products
-      double g[NC];
+      int wv[NC];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) g[i] = s.x[i] * unpack_hi(wo[i * 32]);
+      for (int i = 0; i < NC; ++i) wv[i] = wo[i * 32];
+      const int e_o = wE[r * 32];
+      ctc_step<NC, DIR, false>(s, skipm, pc, nullptr);
+      if (r > 0) load_prow<NC>(pc, pR + (r - 1) * VP8, lam, blank_off);  // next frame's, in flight during the staging
+      const int q_l = s.e + e_o;  // exponent of my lane's products
       if (first) {
         first = false;
         // P = sum over the lattice, combined across lanes at the largest lane exponent
         double sl = 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) sl += g[i];
+        for (int i = 0; i < NC; ++i) sl += s.x[i] * unpack_hi(wv[i]);
         const bool ok = sl > 0.0 && sl < INFINITY;
         const int key = ok ? q_l + expo_hi(__double2hiint(sl)) : E_NONE;
         const int Qm = __reduce_max_sync(FULL, key);
@@ -501,12 +532,19 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
       const double c = feasible ? pow2_flush(kq) * invPm : 0.0;
       double gb = 0.0;
 #pragma unroll
-      for (int i = 0; i < NC; i += 2) gb += g[i];
+      for (int i = 0; i < NC; ++i) {
+        const double pr = s.x[i] * unpack_hi(wv[i]);
+        if (i & 1) {
+          if (spos[i >> 1] >= 0) gf[spos[i >> 1]] = (float)(pr * c);
+        } else {
+          gb += pr;
+        }
+      }
       gf[P.Spad + lane] = (float)(gb * c);
-#pragma unroll
-      for (int k = 0; k < NC / 2; ++k)
-        if (spos[k] >= 0) gf[spos[k]] = (float)(g[2 * k + 1] * c);
-      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) renorm<NC>(s);
+      if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
+        renorm<NC>(s);
+        exchange<NC, DIR>(s);
+      }
     }
     if (want_grad) {
       if (lane == 0) gR[P.Spad + 32] = feasible ? 1.f : 0.f;  // segment flag (frame 0's spare float)
@@ -540,48 +578,96 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
     float* gR = hf.g(ws);
     const double* pR = reinterpret_cast<const double*>(hf.p(ps));
     const bool feasible = gR[P.Spad + 32] != 0.f;
-    for (int r = n - 1; r >= 0; --r, ++tau) {
-      float* gf = gR + (size_t)r * P.GS;
-      const int t = h ? pl.Tb - 1 - tau : tau;
-      float* grow = grow_base + (int64_t)t * P.st;
+    // FR frames at a time: their scans, reductions and loads are independent chains that the
+    // scheduler can interleave, which is what hides the shuffle / shared-memory latencies here
+    constexpr int FR = 3;
+    for (int r = n - 1; r >= 0; r -= FR) {
+      const int nf = r + 1 < FR ? r + 1 : FR;  // frames r, r-1, .., r-nf+1
+      const int tbase = tau + (n - 1 - r);     // local time of frame r
+      float* gfp[FR];
+      float* growp[FR];
+#pragma unroll
+      for (int f = 0; f < FR; ++f) {
+        const int rr = f < nf ? r - f : r;
+        gfp[f] = gR + (size_t)rr * P.GS;
+        const int tt = tbase + (f < nf ? f : 0);
+        growp[f] = grow_base + (int64_t)(h ? pl.Tb - 1 - tt : tt) * P.st;
+      }
       if (feasible) {
-        float gb = gf[P.Spad + lane];
+        float gb[FR], carry[FR];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(FULL, gb, o);
+        for (int f = 0; f < FR; ++f) {
+          gb[f] = gfp[f][P.Spad + lane];
+          carry[f] = 0.f;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+          for (int f = 0; f < FR; ++f) gb[f] += __shfl_xor_sync(FULL, gb[f], o);
         // inclusive prefix sum over the class-sorted label posteriors, in place, 256 per pass
-        float carry = 0.f;
         for (int base = 0; base < S; base += 256) {
-          float4* p4 = reinterpret_cast<float4*>(gf + base + lane * 8);
-          float4 a = p4[0], b = p4[1];
           const int i0 = base + lane * 8;
-          a.x = i0 + 0 < S ? a.x : 0.f; a.y = i0 + 1 < S ? a.y : 0.f; a.z = i0 + 2 < S ? a.z : 0.f; a.w = i0 + 3 < S ? a.w : 0.f;
-          b.x = i0 + 4 < S ? b.x : 0.f; b.y = i0 + 5 < S ? b.y : 0.f; b.z = i0 + 6 < S ? b.z : 0.f; b.w = i0 + 7 < S ? b.w : 0.f;
-          a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
-          float incl = b.w;
+          float4 a[FR], b[FR];
+          float incl[FR], tot8[FR];
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const float y = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += y;
+          for (int f = 0; f < FR; ++f) {
+            const float4* p4 = reinterpret_cast<const float4*>(gfp[f] + i0);
+            a[f] = p4[0];
+            b[f] = p4[1];
           }
-          const float off = carry + incl - b.w;  // everything before my 8
-          a.x += off; a.y += off; a.z += off; a.w += off; b.x += off; b.y += off; b.z += off; b.w += off;
-          p4[0] = a;
-          p4[1] = b;
-          carry += __shfl_sync(FULL, incl, 31);
+#pragma unroll
+          for (int f = 0; f < FR; ++f) {
+            float4 &A = a[f], &B = b[f];
+            A.x = i0 + 0 < S ? A.x : 0.f; A.y = i0 + 1 < S ? A.y : 0.f; A.z = i0 + 2 < S ? A.z : 0.f; A.w = i0 + 3 < S ? A.w : 0.f;
+            B.x = i0 + 4 < S ? B.x : 0.f; B.y = i0 + 5 < S ? B.y : 0.f; B.z = i0 + 6 < S ? B.z : 0.f; B.w = i0 + 7 < S ? B.w : 0.f;
+            A.y += A.x; A.z += A.y; A.w += A.z; B.x += A.w; B.y += B.x; B.z += B.y; B.w += B.z;
+            incl[f] = tot8[f] = B.w;
+          }
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+            for (int f = 0; f < FR; ++f) {
+              const float y = __shfl_up_sync(FULL, incl[f], o);
+              if (lane >= o) incl[f] += y;
+            }
+#pragma unroll
+          for (int f = 0; f < FR; ++f) {
+            const float off = carry[f] + incl[f] - tot8[f];  // everything before my 8
+            float4 &A = a[f], &B = b[f];
+            A.x += off; A.y += off; A.z += off; A.w += off; B.x += off; B.y += off; B.z += off; B.w += off;
+            if (f < nf) {
+              float4* p4 = reinterpret_cast<float4*>(gfp[f] + i0);
+              p4[0] = A;
+              p4[1] = B;
+            }
+            carry[f] += __shfl_sync(FULL, incl[f], 31);
+          }
         }
         __syncwarp();
         for (int v = lane; v < V; v += 32) {
-          const int a = cls[v], b = cls[v + 1];
-          float gv = b > a ? gf[b - 1] - (a > 0 ? gf[a - 1] : 0.f) : 0.f;
-          if (v == P.blank) gv += gb;
-          st_stream(grow + v, ((float)pR[r * VP + v] - gv) * scale);
+          const int ca = cls[v], cb = cls[v + 1];
+          float gv[FR], pv[FR];
+#pragma unroll
+          for (int f = 0; f < FR; ++f) {
+            gv[f] = cb > ca ? gfp[f][cb - 1] - (ca > 0 ? gfp[f][ca - 1] : 0.f) : 0.f;
+            pv[f] = (float)pR[(f < nf ? r - f : r) * VP + v];
+          }
+#pragma unroll
+          for (int f = 0; f < FR; ++f) {
+            if (v == P.blank) gv[f] += gb[f];
+            if (f < nf) st_stream(growp[f] + v, (pv[f] - gv[f]) * scale);
+          }
         }
         __syncwarp();
       } else {
         const float fill = P.zero_inf ? 0.f : NAN;
-        for (int v = lane; v < V; v += 32) st_stream(grow + v, fill);
+#pragma unroll
+        for (int f = 0; f < FR; ++f)
+          if (f < nf)
+            for (int v = lane; v < V; v += 32) st_stream(growp[f] + v, fill);
       }
     }
+    tau += n;
     mbar_arrive(&hf.bar[B_GEMPTY + ws]);
     mbar_arrive(&hf.bar[B_PEMPTY + ps]);
   }
@@ -788,7 +874,7 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
   const int64_t slots = (int64_t)device_sms() * ctas;
   pl.grid = (int)(B < slots ? B : slots);
   pl.nseg_max = (int)((T / 2 + 1 + K - 1) / K + 2);
-  pl.ckpt_rec_bytes = (size_t)pl.NCmax * 32 * 8 + 256;
+  pl.ckpt_rec_bytes = (size_t)pl.NCmax * 32 * 8 + 512;  // strip + per-lane e, z, fin
   pl.ckpt_cta_bytes = (size_t)2 * pl.nseg_max * pl.ckpt_rec_bytes;
   pl.ws_bytes = 256 + (size_t)pl.grid * pl.ckpt_cta_bytes;
   return true;
