@@ -5,9 +5,12 @@
 //
 // Numerics.  The alpha/beta recursions run in the LINEAR domain on fp64 values
 //   alpha_t[s] = (alpha_{t-1}[s] + alpha_{t-1}[s-1] + skip[s] * alpha_{t-1}[s-2]) * p_t[l'_s]
-// (beta: the mirror image, pulling from s+1, s+2).  A lane owns NC consecutive lattice cells in
-// registers together with ONE integer exponent for them (block floating point per lane); every 4
-// frames the lane renormalises its strip by an exact power of two.  Nothing on the recursion needs
+// (beta: the mirror image, pulling from s+1, s+2).  Both sweeps run THE SAME code: a sweep works in
+// "position" space u, with u = s for alpha and u = U - s for beta (U = 32*NC - 2, parity kept), where
+// every position pulls from u-1 and u-2.  One instruction stream per role keeps the hot code of a CTA
+// inside the SM's instruction cache (the first versions were instruction-fetch bound).  A lane owns
+// NC consecutive positions in registers together with ONE integer exponent for them (block floating
+// point per lane); every 8 frames the lane renormalises its strip by an exact power of two.  Nothing on the recursion needs
 // exp/log (ATen's log-space form costs 3-4 MUFU ops per cell) and there is no global dynamic
 // range limit: cells may differ by thousands of binades across the lattice.  p = exp(lp) is
 // evaluated once per (frame, label) with an fp32 mantissa and a full fp64 exponent.
@@ -96,6 +99,8 @@ struct LossParams {
   int Spad;    // label staging capacity, multiple of 256
   int GS;      // floats per staged frame: Spad label posteriors | 32 blank partials | flag
   int use_tma;
+  long long* tlog;  // timeline log (SSD_LOSS_DBG & 8): [role 4][half 2][512][2] clock64 stamps of CTA 0's first utterance
+  int dbg;     // timing experiments only (SSD_LOSS_DBG): 1 G idles, 2 M skips staging, 4 H skips recompute
 };
 
 struct LossSmem {  // byte offsets into dynamic shared memory, identical on host and device
@@ -113,7 +118,7 @@ __host__ __device__ inline LossSmem loss_smem_layout(int K, int NCmax, int V, in
   LossSmem m;
   m.p_slot = al((size_t)K * VP * 8);
   m.w_slot = al((size_t)K * NCmax * 32 * 4);
-  m.we_slot = al((size_t)K * 32 * 4);
+  m.we_slot = al((size_t)K * 64 * 4);
   m.g_slot = al((size_t)K * GS * 4);
   m.raw_slot = al((size_t)K * V * 4);
   size_t o = 0;
@@ -131,6 +136,12 @@ __host__ __device__ inline LossSmem loss_smem_layout(int K, int NCmax, int V, in
   m.scal_off = o; o += 64;
   m.total = o;
   return m;
+}
+
+__device__ __forceinline__ void tstamp(const LossParams& P, int role, int h, int idx, int which, unsigned uiter) {
+#ifndef SSD_EMU
+  if ((P.dbg & 8) && blockIdx.x == 0 && uiter == 0 && idx < 512 && (threadIdx.x & 31) == 0) P.tlog[((role * 2 + h) * 512 + idx) * 2 + which] = clock64();
+#endif
 }
 
 struct LossScal {
@@ -164,33 +175,19 @@ __device__ __forceinline__ void load_prow(PRow<NC>& p, const unsigned char* __re
   for (int k = 0; k < NC / 2; ++k) p.lab[k] = *reinterpret_cast<const double*>(prow + lam[k]);
 }
 
-// DIR 0: cell c pulls from c-1 and (odd c, skip allowed) c-2.  DIR 1: from c+1 and c+2.
-// STORE (helper): also emit the pre-emission sums, packed to 32 bits.
-template <int NC, int DIR, bool STORE>
-__device__ __forceinline__ void ctc_step(Strip<NC>& s, unsigned skipm, const PRow<NC>& p, int* __restrict__ wdst) {
+// One frame of the recursion in position space: u pulls from u-1 and (odd u, skip allowed) u-2.
+// STORE (helper): also emit the pre-emission sums, packed to 32 bits, at the addresses in wofs
+// (the main's layout: position U - u).
+template <int NC, bool STORE>
+__device__ __forceinline__ void ctc_step(Strip<NC>& s, unsigned skipm, const PRow<NC>& p, int* __restrict__ wdst, int wlast) {
   double (&x)[NC] = s.x;
-  double n0, n1 = 0.0;
-  if (DIR == 0) {
-    n0 = __shfl_up_sync(FULL, x[NC - 1], 1);
-    if (lane_id() == 0) n0 = 0.0;
-  } else {
-    n0 = __shfl_down_sync(FULL, x[0], 1);
-    n1 = __shfl_down_sync(FULL, x[1], 1);
-    if (lane_id() == 31) n0 = n1 = 0.0;
-    n1 *= s.fin;
-  }
+  double n0 = __shfl_up_sync(FULL, x[NC - 1], 1);
+  if (lane_id() == 0) n0 = 0.0;
   n0 *= s.fin;
 #pragma unroll
-  for (int ii = 0; ii < NC; ++ii) {
-    const int i = DIR == 0 ? NC - 1 - ii : ii;  // update order keeps the not-yet-read inputs intact
-    double a1, a2;
-    if (DIR == 0) {
-      a1 = (i >= 1) ? x[i >= 1 ? i - 1 : 0] : n0;
-      a2 = (i >= 2) ? x[i >= 2 ? i - 2 : 0] : n0;
-    } else {
-      a1 = (i + 1 < NC) ? x[i + 1 < NC ? i + 1 : 0] : n0;
-      a2 = (i + 2 < NC) ? x[i + 2 < NC ? i + 2 : 0] : n1;  // odd i = NC-1: next lane's cell 1
-    }
+  for (int i = NC - 1; i >= 0; --i) {  // descending: inputs of lower positions are still intact
+    const double a1 = (i >= 1) ? x[i >= 1 ? i - 1 : 0] : n0;
+    const double a2 = (i >= 2) ? x[i >= 2 ? i - 2 : 0] : n0;
     double sum = x[i] + a1;
     if (i & 1) {
       if ((skipm >> (i >> 1)) & 1u) sum += a2;
@@ -198,7 +195,12 @@ __device__ __forceinline__ void ctc_step(Strip<NC>& s, unsigned skipm, const PRo
     } else {
       x[i] = sum * p.blank;
     }
-    if (STORE) wdst[i * 32] = pack_hi(sum);
+    if (STORE) {
+      // my position lane*NC+i is the main's position U-(lane*NC+i): lane 31-lane, register NC-2-i,
+      // except my last register, which lands in register NC-1 of lane 30-lane
+      if (i < NC - 1) wdst[(NC - 2 - i) * 32] = pack_hi(sum);
+      else if (wlast >= 0) wdst[wlast] = pack_hi(sum);
+    }
   }
 }
 
@@ -223,28 +225,21 @@ __device__ __forceinline__ void renorm(Strip<NC>& s) {
   s.z = zero;
 }
 
-// after every renorm: learn the neighbour's exponent and cache the factor for its boundary values.
-// An empty strip takes the exponent of the nearest non-empty strip on the side it pulls from, so
-// that the first mass reaching it lands close to its basis.
-template <int NC, int DIR>
+// after every renorm: learn the lower neighbour's exponent and cache the factor for its boundary
+// value.  An empty strip takes the exponent of the nearest non-empty strip below it, so that the
+// first mass reaching it lands close to its basis.
+template <int NC>
 __device__ __forceinline__ void exchange(Strip<NC>& s) {
   const int lane = lane_id();
   const unsigned live = __ballot_sync(FULL, !s.z);
-  int src;
-  if (DIR == 0) {
-    const unsigned below = live & ((1u << lane) - 1u);
-    src = below ? 31 - __clz((int)below) : lane;
-  } else {
-    const unsigned above = lane == 31 ? 0u : (live >> (lane + 1));
-    src = above ? lane + __ffs((int)above) : lane;
-  }
+  const unsigned below = live & ((1u << lane) - 1u);
+  const int src = below ? 31 - __clz((int)below) : lane;
   const int e_near = __shfl_sync(FULL, s.e, src);
   if (s.z) s.e = e_near;
-  const int ein = DIR == 0 ? __shfl_up_sync(FULL, s.e, 1) : __shfl_down_sync(FULL, s.e, 1);
-  int d = ein - s.e;
-  if ((DIR == 0 && lane == 0) || (DIR == 1 && lane == 31)) d = 0;
+  const int ein = __shfl_up_sync(FULL, s.e, 1);
+  int d = lane == 0 ? 0 : ein - s.e;
   // an empty neighbour's exponent says nothing about what will arrive: never rebase on it
-  const bool nb_live = DIR == 0 ? (lane > 0 && ((live >> (lane - 1)) & 1u)) : (lane < 31 && ((live >> (lane + 1)) & 1u));
+  const bool nb_live = lane > 0 && ((live >> (lane - 1)) & 1u);
   if (!nb_live) d = d > 1000 ? 1000 : d;
   if (d > E_ADOPT && nb_live) {  // neighbour dwarfs me: rebase my strip (rare, divergent)
     const double f = pow2_wide(-d);
@@ -256,33 +251,47 @@ __device__ __forceinline__ void exchange(Strip<NC>& s) {
   s.fin = pow2_flush(d);
 }
 
-// start state of sweep dir: the virtual frame before the first one (one cell = 1)
+// position <-> lattice cell of sweep direction dir:  dir 0: u = s;  dir 1: u = U - s, U = 32*NC - 2
+template <int NC>
+__device__ __forceinline__ int cell_of(int dir, int u) {
+  return dir ? 32 * NC - 2 - u : u;
+}
+
+// start state of a sweep: the virtual frame before the first one (the first cell = 1)
 template <int NC>
 __device__ __forceinline__ void sweep_init(int dir, int L, Strip<NC>& s) {
   const int lane = lane_id();
-  const int cell = dir ? L - 1 : 0;
+  const int u0 = dir ? 32 * NC - 2 - (L - 1) : 0;  // position of cell L-1 (backward) or 0 (forward)
 #pragma unroll
-  for (int i = 0; i < NC; ++i) s.x[i] = (lane * NC + i == cell) ? 1.0 : 0.0;
+  for (int i = 0; i < NC; ++i) s.x[i] = (lane * NC + i == u0) ? 1.0 : 0.0;
   s.e = 0;
-  s.z = (lane != cell / NC);
+  s.z = (lane != u0 / NC);
   s.fin = 1.0;
 }
 
-// per-lane label column offsets (bytes into a p row) and skip mask for sweep direction dir
+// per-lane label column offsets (bytes into a p row), skip mask and (optionally) staging slots for
+// the odd positions of my strip, in sweep direction dir
 template <int NC>
-__device__ __forceinline__ void lane_labels(int dir, int S, int V, const int* __restrict__ lab, int (&lam)[NC / 2], unsigned& skipm) {
+__device__ __forceinline__ void lane_labels(int dir, int S, int V, const int* __restrict__ lab, const int* __restrict__ pos,
+                                            int (&lam)[NC / 2], unsigned& skipm, int* spos) {
   const int lane = lane_id();
+  const int L = 2 * S + 1;
   skipm = 0u;
 #pragma unroll
   for (int k = 0; k < NC / 2; ++k) {
-    const int j = lane * (NC / 2) + k;  // label index of odd cell 2k+1
-    int col = V;                        // dummy column (p = 0) beyond the target
-    if (j < S) {
+    const int u = lane * NC + 2 * k + 1;
+    const int c = cell_of<NC>(dir, u);  // odd, may be out of the lattice
+    int col = V;                        // dummy column (p = 0) outside the target
+    int sp = -1;
+    if (c >= 1 && c < L) {
+      const int j = (c - 1) >> 1;
       col = lab[j];
-      const int jn = dir ? j + 1 : j - 1;  // the label two cells further along the pull direction
-      if (jn >= 0 && jn < S && lab[jn] != col) skipm |= 1u << k;
+      if (pos) sp = pos[j];
+      const int c2 = cell_of<NC>(dir, u - 2);  // the cell two positions back along the sweep
+      if (u >= 2 && c2 >= 1 && c2 < L && lab[(c2 - 1) >> 1] != col) skipm |= 1u << k;
     }
     lam[k] = col * 8;
+    if (spos) spos[k] = sp;
   }
 }
 
@@ -321,7 +330,7 @@ struct Plan {  // per utterance, per half
 };
 
 // ------------------------------------------------------------------ L: loader / converter
-__device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl, unsigned qbase, unsigned jbase) {
+__device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl, unsigned qbase, unsigned jbase, unsigned uiter) {
   const int lane = lane_id();
   const int K = P.K, V = P.V, VP = P.VP;
   const float* base = P.lp + (int64_t)pl.b * P.sb;
@@ -343,6 +352,7 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
     const unsigned Q = qbase + (unsigned)q;
     const int slot = (int)(Q % LS_NP);
     mbar_wait(&hf.bar[B_PEMPTY + slot], ((Q / LS_NP) & 1u) ^ 1u);
+    tstamp(P, 2, pl.h, q, 0, uiter);
     const Prod pd = prod_desc(q, pl.h, pl.m_h, pl.m_o, K, pl.NP1, pl.NSEG);
     double* pR = reinterpret_cast<double*>(hf.p(slot));
     // row r of the slot <-> local time tau0 + r of direction pd.dir
@@ -367,19 +377,24 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
     }
     if (lane < pd.n) pR[lane * VP + V] = 0.0;  // dummy column (K <= 32)
     mbar_arrive(&hf.bar[B_PFULL + slot]);
+    tstamp(P, 2, pl.h, q, 1, uiter);
     if (q >= pl.NP1) mbar_arrive(&hf.bar[B_HPFULL + (int)((jbase + (unsigned)(q - pl.NP1)) % LS_NP)]);  // the helper's view
   }
 }
 
 // ------------------------------------------------------------------ H: recompute helper (phase 2 only)
-template <int NC, int DIR>
+template <int NC>
 __device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ lab, uint64_t* p1done_other,
                             unsigned uiter, unsigned qbase, unsigned jbase, const unsigned char* ckpt_cta) {
   const int lane = lane_id();
   const int K = P.K, VP8 = P.VP * 8, blank_off = P.blank * 8;
+  const int dir = pl.h ^ 1;  // I re-compute the OTHER sweep
   int lam[NC / 2];
   unsigned skipm;
-  lane_labels<NC>(DIR, pl.S, P.V, lab, lam, skipm);
+  lane_labels<NC>(dir, pl.S, P.V, lab, nullptr, lam, skipm, nullptr);
+  // where my sums go in the main's layout (see ctc_step)
+  const int wbase = 31 - lane;
+  const int wlast = lane < 31 ? (NC - 1) * 32 + (30 - lane) : -1;
   Strip<NC> s;
   for (int j = 0; j < pl.NSEG_RUN; ++j) {
     const unsigned Q = qbase + (unsigned)(pl.NP1 + j), J = jbase + (unsigned)j;
@@ -389,55 +404,55 @@ __device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl,
     // I skip the phase-1 productions, so p_full's parity could alias by the time I get here.
     mbar_wait(&hf.bar[B_HPFULL + (int)(J % LS_NP)], (J / LS_NP) & 1u);
     mbar_wait(&hf.bar[B_WEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    tstamp(P, 1, pl.h, pl.NP1 + j, 0, uiter);
     const int seg = pl.NSEG - 1 - j;
     const int tau0 = seg * K, n = min(K, pl.m_o - tau0);
     if (seg == 0) {
-      sweep_init<NC>(DIR, pl.L, s);
+      sweep_init<NC>(dir, pl.L, s);
     } else {
-      const unsigned char* cp = ckpt_cta + ((size_t)DIR * P.nseg_max + seg) * P.ckpt_rec_bytes;
+      const unsigned char* cp = ckpt_cta + ((size_t)dir * P.nseg_max + seg) * P.ckpt_rec_bytes;
       const double* cx = reinterpret_cast<const double*>(cp);
 #pragma unroll
       for (int i = 0; i < NC; ++i) s.x[i] = cx[i * 32 + lane];
-      const int* ce = reinterpret_cast<const int*>(cp + (size_t)P.NCmax * 32 * 8);
+      const int* ce = reinterpret_cast<const int*>(cp + (size_t)NC * 32 * 8);
       s.e = ce[lane];
       s.z = ce[32 + lane] != 0;
       s.fin = reinterpret_cast<const double*>(ce + 64)[lane];
     }
     const unsigned char* pR = hf.p(ps);
-    int* wR = hf.w(ws) + lane;
-    int* wE = hf.we(ws) + lane;
+    int* wR = hf.w(ws);
+    int* wE = hf.we(ws);
     int tau = tau0;
     PRow<NC> pc;
     load_prow<NC>(pc, pR, lam, blank_off);
     for (int r = 0; r < n; ++r, ++tau) {
-      ctc_step<NC, DIR, true>(s, skipm, pc, wR + r * NC * 32);
+      ctc_step<NC, true>(s, skipm, pc, wR + r * NC * 32 + wbase, wlast - wbase);
       if (r + 1 < n) load_prow<NC>(pc, pR + (r + 1) * VP8, lam, blank_off);  // next frame's, in flight during the rest
-      wE[r * 32] = s.e;  // basis of the sums just stored
+      // basis of the sums just stored: exponent A of main lane 31-lane, exponent B of main lane 30-lane
+      wE[r * 64 + 2 * (31 - lane)] = s.e;
+      if (lane < 31) wE[r * 64 + 2 * (30 - lane) + 1] = s.e;
       if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
         renorm<NC>(s);
-        exchange<NC, DIR>(s);
+        exchange<NC>(s);
       }
     }
     mbar_arrive(&hf.bar[B_WFULL + ws]);
+    tstamp(P, 1, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
 
 // ------------------------------------------------------------------ M: main sweep
-template <int NC, int DIR>
+template <int NC>
 __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ lab, const int* __restrict__ pos,
-                          uint64_t* p1done_mine, unsigned qbase, unsigned jbase, unsigned char* ckpt_cta) {
+                          uint64_t* p1done_mine, unsigned qbase, unsigned jbase, unsigned char* ckpt_cta, unsigned uiter) {
   const int lane = lane_id();
   const int K = P.K, VP8 = P.VP * 8, blank_off = P.blank * 8;
+  const int dir = pl.h;
   int lam[NC / 2], spos[NC / 2];
   unsigned skipm;
-  lane_labels<NC>(DIR, pl.S, P.V, lab, lam, skipm);
-#pragma unroll
-  for (int k = 0; k < NC / 2; ++k) {
-    const int j = lane * (NC / 2) + k;
-    spos[k] = j < pl.S ? pos[j] : -1;
-  }
+  lane_labels<NC>(dir, pl.S, P.V, lab, pos, lam, skipm, spos);
   Strip<NC> s;
-  sweep_init<NC>(DIR, pl.L, s);
+  sweep_init<NC>(dir, pl.L, s);
   int tau = 0;
 
   // ---------------- phase 1: my half of the frames, checkpoint every K
@@ -445,25 +460,27 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     const unsigned Q = qbase + (unsigned)q;
     const int ps = (int)(Q % LS_NP);
     mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    tstamp(P, 0, pl.h, q, 0, uiter);
     const unsigned char* pR = hf.p(ps);
     const int n = min(K, pl.m_h - q * K);
     PRow<NC> pc;
     load_prow<NC>(pc, pR, lam, blank_off);
     for (int r = 0; r < n; ++r, ++tau) {
-      ctc_step<NC, DIR, false>(s, skipm, pc, nullptr);
+      ctc_step<NC, false>(s, skipm, pc, nullptr, 0);
       if (r + 1 < n) load_prow<NC>(pc, pR + (r + 1) * VP8, lam, blank_off);  // next frame's, in flight during the rest
       if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
         renorm<NC>(s);
-        exchange<NC, DIR>(s);
+        exchange<NC>(s);
       }
     }
     mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    tstamp(P, 0, pl.h, q, 1, uiter);
     if (q + 1 < pl.NP1) {  // state after frame (q+1)K-1 starts segment q+1
-      unsigned char* cp = ckpt_cta + ((size_t)DIR * P.nseg_max + (q + 1)) * P.ckpt_rec_bytes;
+      unsigned char* cp = ckpt_cta + ((size_t)dir * P.nseg_max + (q + 1)) * P.ckpt_rec_bytes;
       double* cx = reinterpret_cast<double*>(cp);
 #pragma unroll
       for (int i = 0; i < NC; ++i) cx[i * 32 + lane] = s.x[i];
-      int* ce = reinterpret_cast<int*>(cp + (size_t)P.NCmax * 32 * 8);
+      int* ce = reinterpret_cast<int*>(cp + (size_t)NC * 32 * 8);
       ce[lane] = s.e;
       ce[32 + lane] = s.z ? 1 : 0;
       reinterpret_cast<double*>(ce + 64)[lane] = s.fin;
@@ -485,28 +502,33 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     mbar_wait(&hf.bar[B_WFULL + ws], (J >> 1) & 1u);
     mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
     if (want_grad) mbar_wait(&hf.bar[B_GEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    tstamp(P, 0, pl.h, pl.NP1 + j, 0, uiter);
     const unsigned char* pR = hf.p(ps);
     const int* wR = hf.w(ws) + lane;
-    const int* wE = hf.we(ws) + lane;
+    const int* wE = hf.we(ws) + 2 * lane;
     float* gR = hf.g(ws);
     PRow<NC> pc;
     load_prow<NC>(pc, pR + (n - 1) * VP8, lam, blank_off);
     for (int r = n - 1; r >= 0; --r, ++tau) {
-      // the other sweep's sums for my cells (issued before the step so their latency is covered)
+      // the other sweep's sums for my positions (issued before the step so their latency is covered)
       const int* wo = wR + r * NC * 32;
       int wv[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) wv[i] = wo[i * 32];
-      const int e_o = wE[r * 32];
-      ctc_step<NC, DIR, false>(s, skipm, pc, nullptr);
+      if (lane == 31) wv[NC - 1] = 0;  // position 32*NC-1 belongs to no cell
+      const int e_a = wE[r * 64], e_b = wE[r * 64 + 1];  // bases of registers 0..NC-2 / NC-1
+      ctc_step<NC, false>(s, skipm, pc, nullptr, 0);
       if (r > 0) load_prow<NC>(pc, pR + (r - 1) * VP8, lam, blank_off);  // next frame's, in flight during the staging
-      const int q_l = s.e + e_o;  // exponent of my lane's products
+      const int q_l = s.e + e_a;  // exponent of my lane's products
+      int db = e_b - e_a;
+      db = db > 1000 ? 1000 : db;
+      const double f_b = lane == 31 ? 0.0 : pow2_flush(db);  // brings register NC-1's product into that basis
       if (first) {
         first = false;
         // P = sum over the lattice, combined across lanes at the largest lane exponent
         double sl = 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) sl += s.x[i] * unpack_hi(wv[i]);
+        for (int i = 0; i < NC; ++i) sl += s.x[i] * unpack_hi(wv[i]) * (i == NC - 1 ? f_b : 1.0);
         const bool ok = sl > 0.0 && sl < INFINITY;
         const int key = ok ? q_l + expo_hi(__double2hiint(sl)) : E_NONE;
         const int Qm = __reduce_max_sync(FULL, key);
@@ -519,8 +541,8 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
           const double pm = tot * pow2_wide(-et);  // in [1,2)
           invPm = 1.0 / pm;
           eP = Qm + et;
-          if (DIR == 0 && lane == 0) P.nll[pl.b] = (float)(-(log(pm) + (double)eP * 0.69314718055994530942));
-        } else if (DIR == 0 && lane == 0) {
+          if (dir == 0 && lane == 0) P.nll[pl.b] = (float)(-(log(pm) + (double)eP * 0.69314718055994530942));
+        } else if (dir == 0 && lane == 0) {
           P.nll[pl.b] = P.zero_inf ? 0.f : INFINITY;
         }
         if (!want_grad) break;
@@ -535,7 +557,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
       for (int i = 0; i < NC; ++i) {
         const double pr = s.x[i] * unpack_hi(wv[i]);
         if (i & 1) {
-          if (spos[i >> 1] >= 0) gf[spos[i >> 1]] = (float)(pr * c);
+          if (spos[i >> 1] >= 0) gf[spos[i >> 1]] = (float)(pr * (i == NC - 1 ? c * f_b : c));
         } else {
           gb += pr;
         }
@@ -543,7 +565,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
       gf[P.Spad + lane] = (float)(gb * c);
       if ((tau & (LS_RESCALE - 1)) == LS_RESCALE - 1) {
         renorm<NC>(s);
-        exchange<NC, DIR>(s);
+        exchange<NC>(s);
       }
     }
     if (want_grad) {
@@ -552,13 +574,14 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     }
     mbar_arrive(&hf.bar[B_WEMPTY + ws]);
     mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    tstamp(P, 0, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
 
 // ------------------------------------------------------------------ G: gradient writer
 // Takes part in every production's release (p_empty) so that the loader can never lap it.
 __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, const int* __restrict__ cls, float scale, unsigned qbase,
-                          unsigned jbase) {
+                          unsigned jbase, unsigned uiter) {
   const int lane = lane_id();
   const int K = P.K, V = P.V, S = pl.S, h = pl.h, VP = P.VP;
   float* grow_base = P.grad + (int64_t)pl.b * P.sb;
@@ -575,6 +598,7 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
     const int seg = pl.NSEG - 1 - j;
     const int n = min(K, pl.m_o - seg * K);
     mbar_wait(&hf.bar[B_GFULL + ws], (J >> 1) & 1u);  // implies the rows of production Q are in place
+    tstamp(P, 3, pl.h, pl.NP1 + j, 0, uiter);
     float* gR = hf.g(ws);
     const double* pR = reinterpret_cast<const double*>(hf.p(ps));
     const bool feasible = gR[P.Spad + 32] != 0.f;
@@ -670,11 +694,12 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
     tau += n;
     mbar_arrive(&hf.bar[B_GEMPTY + ws]);
     mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    tstamp(P, 3, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
 
 // ------------------------------------------------------------------ kernel
-template <int NCMAX, int MINB>
+template <int NC, int MINB>
 __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams P) {
   SSD_DYN_SMEM(smem);
   const LossSmem M = loss_smem_layout(P.K, P.NCmax, P.V, P.VP, P.GS, P.S_max + 4);
@@ -779,33 +804,14 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
     // forward only: just the first phase-2 frame of the forward half is needed (it yields P)
     pl.NSEG_RUN = P.grad ? pl.NSEG : (h == 0 ? min(pl.NSEG, 1) : 0);
     pl.NPROD = pl.NP1 + pl.NSEG_RUN;
-    const int nc_need = (pl.L + 31) / 32;
-
     if (role == 2) {
-      loader_role(P, hf, pl, qbase, jbase);
+      loader_role(P, hf, pl, qbase, jbase, uiter);
     } else if (role == 3) {
-      if (P.grad) grad_role(P, hf, pl, cls, scale, qbase, jbase);
+      if (P.grad) grad_role(P, hf, pl, cls, scale, qbase, jbase, uiter);
+    } else if (role == 1) {
+      helper_role<NC>(P, hf, pl, lab, &p1done[h ^ 1], uiter, qbase, jbase, ckpt_cta);  // re-computes direction h^1
     } else {
-      // main of half h sweeps direction h; its helper re-computes direction h^1
-#define SSD_ROLE(NCV)                                                                                              \
-  do {                                                                                                             \
-    if (role == 1) {                                                                                               \
-      if (h == 0) helper_role<NCV, 1>(P, hf, pl, lab, &p1done[1], uiter, qbase, jbase, ckpt_cta);                   \
-      else helper_role<NCV, 0>(P, hf, pl, lab, &p1done[0], uiter, qbase, jbase, ckpt_cta);                          \
-    } else {                                                                                                       \
-      if (h == 0) main_role<NCV, 0>(P, hf, pl, lab, pos, &p1done[0], qbase, jbase, ckpt_cta);                       \
-      else main_role<NCV, 1>(P, hf, pl, lab, pos, &p1done[1], qbase, jbase, ckpt_cta);                              \
-    }                                                                                                              \
-  } while (0)
-      if constexpr (NCMAX <= 14) {
-        if (nc_need <= 4) SSD_ROLE(4);
-        else if (nc_need <= 8) SSD_ROLE(8);
-        else SSD_ROLE(14);
-      } else {
-        if (nc_need <= 20) SSD_ROLE(20);
-        else SSD_ROLE(32);
-      }
-#undef SSD_ROLE
+      main_role<NC>(P, hf, pl, lab, pos, &p1done[h], qbase, jbase, ckpt_cta, uiter);  // sweeps direction h
     }
     qbase += (unsigned)pl.NPROD;
     jbase += (unsigned)pl.NSEG_RUN;
@@ -836,9 +842,14 @@ static int device_sms() {
 }
 
 static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& pl) {
-  const int need = (int)((2 * S_max + 1 + 31) / 32);
-  if (need > 32) return false;
-  pl.NCmax = need <= 14 ? 14 : 32;
+  // one code variant per launch, chosen from the widest possible lattice: 2*S_max+1 cells plus the
+  // unused top position must fit 32*NC positions
+  const int need = (int)((2 * S_max + 2 + 31) / 32);
+  const int buckets[5] = {4, 8, 14, 20, 32};
+  pl.NCmax = 0;
+  for (int i = 0; i < 5 && !pl.NCmax; ++i)
+    if (need <= buckets[i]) pl.NCmax = buckets[i];
+  if (!pl.NCmax) return false;
   pl.VP = (int)((V + 2) & ~1LL);
   pl.Spad = (int)((S_max + 255) / 256 * 256);
   if (pl.Spad == 0) pl.Spad = 256;
@@ -876,7 +887,7 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
   pl.nseg_max = (int)((T / 2 + 1 + K - 1) / K + 2);
   pl.ckpt_rec_bytes = (size_t)pl.NCmax * 32 * 8 + 512;  // strip + per-lane e, z, fin
   pl.ckpt_cta_bytes = (size_t)2 * pl.nseg_max * pl.ckpt_rec_bytes;
-  pl.ws_bytes = 256 + (size_t)pl.grid * pl.ckpt_cta_bytes;
+  pl.ws_bytes = 256 + (size_t)pl.grid * pl.ckpt_cta_bytes + 8 * 512 * 2 * 8;  // + timeline log
   return true;
 }
 
@@ -885,9 +896,9 @@ size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
   return plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 256;
 }
 
-template <int NCMAX, int MINB>
+template <int NC, int MINB>
 static int loss_launch_t(LossParams& P, const LossPlan& pl, cudaStream_t stream) {
-  auto kfn = loss_kernel<NCMAX, MINB>;
+  auto kfn = loss_kernel<NC, MINB>;
 #ifndef SSD_EMU
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
@@ -920,7 +931,16 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nseg_max = pl.nseg_max;
   P.K = pl.K; P.NCmax = pl.NCmax; P.VP = pl.VP; P.Spad = pl.Spad; P.GS = pl.GS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
-  return pl.NCmax <= 14 ? loss_launch_t<14, 2>(P, pl, stream) : loss_launch_t<32, 1>(P, pl, stream);
+  if (env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;  // tuning knob
+  P.dbg = env_int("SSD_LOSS_DBG", 0);
+  P.tlog = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ws) + pl.ws_bytes - 8 * 512 * 2 * 8);
+  switch (pl.NCmax) {
+    case 4: return loss_launch_t<4, 2>(P, pl, stream);
+    case 8: return loss_launch_t<8, 2>(P, pl, stream);
+    case 14: return loss_launch_t<14, 2>(P, pl, stream);
+    case 20: return loss_launch_t<20, 1>(P, pl, stream);
+    default: return loss_launch_t<32, 1>(P, pl, stream);
+  }
 }
 
 }  // namespace ssd
