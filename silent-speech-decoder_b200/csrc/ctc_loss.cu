@@ -64,13 +64,23 @@ __device__ __forceinline__ double pow2_wide(int e) {
 // the shared-memory format of the helper's sums -- full fp64 range at 4 bytes per cell.
 __device__ __forceinline__ int pack_hi(double v) { return __double2hiint(v) + (int)((unsigned)__double2loint(v) >> 31); }
 __device__ __forceinline__ double unpack_hi(int h) { return __hiloint2double(h, 0); }
+// 2^x for x in [0,1): one MUFU.EX2, no range handling needed
+__device__ __forceinline__ float ex2_unit(float x) {
+#ifdef SSD_EMU
+  return exp2f(x);
+#else
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
+}
 // exp(lp) as a double: fp32 mantissa (one ex2 on the fractional part) but the exponent goes straight
 // into the fp64 exponent field, so log-probs down to -700 stay non-zero (fp32 exp dies at -87)
 __device__ __forceinline__ double prob_of(float lp) {
   const float t = lp * 1.4426950408889634f;
   if (!(t > -1000.f)) return 0.0;  // also catches -inf and NaN
   const float k = floorf(t);
-  const double m = (double)exp2f(t - k);  // [1,2]
+  const double m = (double)ex2_unit(t - k);  // [1,2]
   return __hiloint2double(__double2hiint(m) + ((int)k << 20), __double2loint(m));
 }
 
@@ -142,6 +152,16 @@ __device__ __forceinline__ void tstamp(const LossParams& P, int role, int h, int
 #ifndef SSD_EMU
   if ((P.dbg & 8) && blockIdx.x == 0 && uiter == 0 && idx < 512 && (threadIdx.x & 31) == 0) P.tlog[((role * 2 + h) * 512 + idx) * 2 + which] = clock64();
 #endif
+}
+
+// warp-level hand-off: one lane talks to the mbarrier, __syncwarp orders the other lanes' shared-memory
+// accesses around it (32x fewer atomics and polls than every lane arriving / waiting)
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);  // every lane: try_wait parks the whole warp in hardware and wakes it promptly
+}
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if (lane_id() == 0) mbar_arrive(bar);
 }
 
 struct LossScal {
@@ -351,14 +371,14 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
     if (P.use_tma && lane == 0 && q + LS_NRAW - 1 < pl.NPROD) issue_raw(q + LS_NRAW - 1);
     const unsigned Q = qbase + (unsigned)q;
     const int slot = (int)(Q % LS_NP);
-    mbar_wait(&hf.bar[B_PEMPTY + slot], ((Q / LS_NP) & 1u) ^ 1u);
+    warp_wait(&hf.bar[B_PEMPTY + slot], ((Q / LS_NP) & 1u) ^ 1u);
     tstamp(P, 2, pl.h, q, 0, uiter);
     const Prod pd = prod_desc(q, pl.h, pl.m_h, pl.m_o, K, pl.NP1, pl.NSEG);
     double* pR = reinterpret_cast<double*>(hf.p(slot));
     // row r of the slot <-> local time tau0 + r of direction pd.dir
     if (P.use_tma) {
       const int rs = (int)(Q % LS_NRAW);
-      mbar_wait(&hf.bar[B_RAW + rs], (Q / LS_NRAW) & 1u);
+      warp_wait(&hf.bar[B_RAW + rs], (Q / LS_NRAW) & 1u);
       const float4* raw4 = reinterpret_cast<const float4*>(hf.raw(rs));
       for (int idx = lane; idx < pd.n * V4; idx += 32) {  // V % 4 == 0 on this path
         const int br = idx / V4, c4 = idx - br * V4;
@@ -376,9 +396,9 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
       }
     }
     if (lane < pd.n) pR[lane * VP + V] = 0.0;  // dummy column (K <= 32)
-    mbar_arrive(&hf.bar[B_PFULL + slot]);
+    warp_arrive(&hf.bar[B_PFULL + slot]);
     tstamp(P, 2, pl.h, q, 1, uiter);
-    if (q >= pl.NP1) mbar_arrive(&hf.bar[B_HPFULL + (int)((jbase + (unsigned)(q - pl.NP1)) % LS_NP)]);  // the helper's view
+    if (q >= pl.NP1) warp_arrive(&hf.bar[B_HPFULL + (int)((jbase + (unsigned)(q - pl.NP1)) % LS_NP)]);  // the helper's view
   }
 }
 
@@ -399,11 +419,11 @@ __device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl,
   for (int j = 0; j < pl.NSEG_RUN; ++j) {
     const unsigned Q = qbase + (unsigned)(pl.NP1 + j), J = jbase + (unsigned)j;
     const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
-    if (j == 0) mbar_wait(p1done_other, uiter & 1u);  // the other main has published its checkpoints
+    if (j == 0) warp_wait(p1done_other, uiter & 1u);  // the other main has published its checkpoints
     // rows of production Q are ready.  A barrier of my own (armed for phase-2 productions only):
     // I skip the phase-1 productions, so p_full's parity could alias by the time I get here.
-    mbar_wait(&hf.bar[B_HPFULL + (int)(J % LS_NP)], (J / LS_NP) & 1u);
-    mbar_wait(&hf.bar[B_WEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    warp_wait(&hf.bar[B_HPFULL + (int)(J % LS_NP)], (J / LS_NP) & 1u);
+    warp_wait(&hf.bar[B_WEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
     tstamp(P, 1, pl.h, pl.NP1 + j, 0, uiter);
     const int seg = pl.NSEG - 1 - j;
     const int tau0 = seg * K, n = min(K, pl.m_o - tau0);
@@ -436,7 +456,7 @@ __device__ void helper_role(const LossParams& P, const Half& hf, const Plan& pl,
         exchange<NC>(s);
       }
     }
-    mbar_arrive(&hf.bar[B_WFULL + ws]);
+    warp_arrive(&hf.bar[B_WFULL + ws]);
     tstamp(P, 1, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
@@ -459,7 +479,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
   for (int q = 0; q < pl.NP1; ++q) {
     const unsigned Q = qbase + (unsigned)q;
     const int ps = (int)(Q % LS_NP);
-    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    warp_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
     tstamp(P, 0, pl.h, q, 0, uiter);
     const unsigned char* pR = hf.p(ps);
     const int n = min(K, pl.m_h - q * K);
@@ -473,7 +493,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
         exchange<NC>(s);
       }
     }
-    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    warp_arrive(&hf.bar[B_PEMPTY + ps]);
     tstamp(P, 0, pl.h, q, 1, uiter);
     if (q + 1 < pl.NP1) {  // state after frame (q+1)K-1 starts segment q+1
       unsigned char* cp = ckpt_cta + ((size_t)dir * P.nseg_max + (q + 1)) * P.ckpt_rec_bytes;
@@ -487,7 +507,7 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     }
   }
   __threadfence_block();
-  mbar_arrive(p1done_mine);
+  warp_arrive(p1done_mine);
 
   // ---------------- phase 2: the other half; posteriors = mine (post-emission) x other's (pre-emission)
   bool first = true, feasible = true;
@@ -499,9 +519,9 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
     const int seg = pl.NSEG - 1 - j;
     const int n = min(K, pl.m_o - seg * K);
-    mbar_wait(&hf.bar[B_WFULL + ws], (J >> 1) & 1u);
-    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
-    if (want_grad) mbar_wait(&hf.bar[B_GEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
+    warp_wait(&hf.bar[B_WFULL + ws], (J >> 1) & 1u);
+    warp_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    if (want_grad) warp_wait(&hf.bar[B_GEMPTY + ws], ((J >> 1) & 1u) ^ 1u);
     tstamp(P, 0, pl.h, pl.NP1 + j, 0, uiter);
     const unsigned char* pR = hf.p(ps);
     const int* wR = hf.w(ws) + lane;
@@ -570,10 +590,10 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
     }
     if (want_grad) {
       if (lane == 0) gR[P.Spad + 32] = feasible ? 1.f : 0.f;  // segment flag (frame 0's spare float)
-      mbar_arrive(&hf.bar[B_GFULL + ws]);
+      warp_arrive(&hf.bar[B_GFULL + ws]);
     }
-    mbar_arrive(&hf.bar[B_WEMPTY + ws]);
-    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    warp_arrive(&hf.bar[B_WEMPTY + ws]);
+    warp_arrive(&hf.bar[B_PEMPTY + ps]);
     tstamp(P, 0, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
@@ -588,8 +608,8 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
   for (int q = 0; q < pl.NP1; ++q) {  // phase 1: nothing to write yet, just keep in step
     const unsigned Q = qbase + (unsigned)q;
     const int ps = (int)(Q % LS_NP);
-    mbar_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
-    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    warp_wait(&hf.bar[B_PFULL + ps], (Q / LS_NP) & 1u);
+    warp_arrive(&hf.bar[B_PEMPTY + ps]);
   }
   int tau = pl.m_h;
   for (int j = 0; j < pl.NSEG_RUN; ++j) {
@@ -597,7 +617,7 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
     const int ps = (int)(Q % LS_NP), ws = (int)(J & 1u);
     const int seg = pl.NSEG - 1 - j;
     const int n = min(K, pl.m_o - seg * K);
-    mbar_wait(&hf.bar[B_GFULL + ws], (J >> 1) & 1u);  // implies the rows of production Q are in place
+    warp_wait(&hf.bar[B_GFULL + ws], (J >> 1) & 1u);  // implies the rows of production Q are in place
     tstamp(P, 3, pl.h, pl.NP1 + j, 0, uiter);
     float* gR = hf.g(ws);
     const double* pR = reinterpret_cast<const double*>(hf.p(ps));
@@ -692,8 +712,8 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
       }
     }
     tau += n;
-    mbar_arrive(&hf.bar[B_GEMPTY + ws]);
-    mbar_arrive(&hf.bar[B_PEMPTY + ps]);
+    warp_arrive(&hf.bar[B_GEMPTY + ws]);
+    warp_arrive(&hf.bar[B_PEMPTY + ps]);
     tstamp(P, 3, pl.h, pl.NP1 + j, 1, uiter);
   }
 }
@@ -704,7 +724,9 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
   SSD_DYN_SMEM(smem);
   const LossSmem M = loss_smem_layout(P.K, P.NCmax, P.V, P.VP, P.GS, P.S_max + 4);
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int h = warp & 1, role = warp >> 1;  // 0 M, 1 H, 2 L, 3 G
+  // warp -> (role, half).  Scheduler partition = warp % 4: M_0+G_0 | M_1+G_1 | H_0+L_0 | H_1+L_1, so in
+  // phase 1 (only M and L busy) the mains do not share an issue port with the loaders
+  const int h = warp & 1, role = warp >> 1;  // 0 M, 1 H, 2 G, 3 L
 
   int* lab = reinterpret_cast<int*>(smem + M.lab_off);
   int* pos = reinterpret_cast<int*>(smem + M.pos_off);
@@ -722,13 +744,13 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
   if (tid == 0) {
     for (int hh = 0; hh < 2; ++hh) {
       uint64_t* b = bars + hh * B_PER_HALF;
-      for (int i = 0; i < B_RAW; ++i) mbar_init(&b[i], 32);  // one arrival per lane of the arriving warp
+      for (int i = 0; i < B_RAW; ++i) mbar_init(&b[i], 1);  // one arrival per arriving warp
       if (P.grad)
-        for (int i = 0; i < LS_NP; ++i) mbar_init(&b[B_PEMPTY + i], 64);  // rows are released by M and G
+        for (int i = 0; i < LS_NP; ++i) mbar_init(&b[B_PEMPTY + i], 2);  // rows are released by M and G
       for (int i = 0; i < LS_NRAW; ++i) mbar_init(&b[B_RAW + i], 1);  // lane 0 + tx bytes
     }
-    mbar_init(&p1done[0], 32);
-    mbar_init(&p1done[1], 32);
+    mbar_init(&p1done[0], 1);
+    mbar_init(&p1done[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -804,9 +826,9 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
     // forward only: just the first phase-2 frame of the forward half is needed (it yields P)
     pl.NSEG_RUN = P.grad ? pl.NSEG : (h == 0 ? min(pl.NSEG, 1) : 0);
     pl.NPROD = pl.NP1 + pl.NSEG_RUN;
-    if (role == 2) {
+    if (role == 3) {
       loader_role(P, hf, pl, qbase, jbase, uiter);
-    } else if (role == 3) {
+    } else if (role == 2) {
       if (P.grad) grad_role(P, hf, pl, cls, scale, qbase, jbase, uiter);
     } else if (role == 1) {
       helper_role<NC>(P, hf, pl, lab, &p1done[h ^ 1], uiter, qbase, jbase, ckpt_cta);  // re-computes direction h^1
