@@ -30,7 +30,10 @@
 
 namespace ssd {
 
-constexpr int BM_CONS = 128;             // consumer threads (warps 0-3)
+#ifndef SSD_BEAM_CONS
+#define SSD_BEAM_CONS 64
+#endif
+constexpr int BM_CONS = SSD_BEAM_CONS;    // consumer threads (a per-frame phase rarely has more than ~100 items)
 constexpr int BM_THREADS = BM_CONS + 32;  // + producer warp
 constexpr int BM_CHUNK = 16;             // frames per TMA chunk
 constexpr int BAR_CONS = 1;              // named barrier: consumers only
@@ -72,6 +75,12 @@ __host__ __device__ inline int beam_table_slots(int W) {
   int ts = 64;
   while (ts < 4 * W) ts <<= 1;
   return ts;
+}
+
+// barrier among the consumer threads: a warp barrier when there is a single consumer warp
+__device__ __forceinline__ void cons_sync() {
+  if (BM_CONS == 32) __syncwarp();
+  else bar_sync(BAR_CONS, BM_CONS);
 }
 
 // ------------------------------------------------------------------ small device helpers
@@ -148,6 +157,8 @@ __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, 
   s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
   s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // candidate score, desc
   s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // alive score, alive idx
+  s += 2 * al(4 * (size_t)NCAND) + al(4 * 256);             // bucket of each alive entry, boundary list, histogram
+  s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // the W survivors of the bucket cut
   s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
   s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // sel_hk, sel_lc
   s += 2 * (al(4 * (size_t)VL) + al(VL));                   // frame records: rl[VL], cs[VL] (x2)
@@ -169,6 +180,7 @@ struct Scal {
   int np;
   int n_e3;
   int n_alive;
+  int n_b, beta, c0;
   int n_sel;
   int n_keep_old;
   int n_new;
@@ -289,7 +301,7 @@ __device__ __forceinline__ int table_find(const unsigned long long* keys, const 
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
+__global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
   const int W = P.W, VL = P.VL, TS = P.TS, NCAND = P.NCAND;
@@ -313,6 +325,11 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
   uint32_t* cdesc = (uint32_t*)carve(sp, 4 * NCAND);
   double* ascore = (double*)carve(sp, 8 * NCAND);
   int* aidx = (int*)carve(sp, 4 * NCAND);
+  int* abkt = (int*)carve(sp, 4 * NCAND);
+  int* blist = (int*)carve(sp, 4 * NCAND);
+  int* hist = (int*)carve(sp, 4 * 256);
+  double* bscore = (double*)carve(sp, 8 * (W + 1));
+  int* bidx = (int*)carve(sp, 4 * (W + 1));
   int* sel = (int*)carve(sp, 4 * (W + 1));
   int* sel_keep = (int*)carve(sp, 4 * (W + 1));
   int* sel_slot = (int*)carve(sp, 4 * (W + 1));
@@ -450,7 +467,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
         par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 2: rank by tot; per-prefix entries
       const float r_blank = F.rl[0];
@@ -478,7 +495,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         int J = W / (rk + 1) + 1;
         rowoff[rk] = J < nc1 ? J : nc1;
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 2b: exclusive scan of row widths (warp 0)
       if (warp == 0) {
@@ -497,7 +514,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         }
         if (lane == 0) sc->n_e3 = carry;
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 3: candidate entries
       const int n_e3 = sc->n_e3;
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         cscore[k] = s;
         cdesc[k] = d;
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 4a: block max
       {
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         m = warp_max_d(m);
         if (lane == 0) sc->wmax[warp] = m;
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
       double cutoff;
       {
         double m = sc->wmax[0];
@@ -559,7 +576,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
           const bool alive = k < ncand && cscore[k] >= cutoff && cscore[k] != -INFINITY;
           const unsigned m = __ballot_sync(FULL, alive);
           if (lane == 0) sc->wcnt[warp] = __popc(m);
-          bar_sync(BAR_CONS, BM_CONS);
+          cons_sync();
           int off = running, totc = 0;
 #pragma unroll
           for (int w = 0; w < BM_CONS / 32; ++w) {
@@ -573,24 +590,111 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
             aidx[pos] = k;
           }
           running += totc;
-          bar_sync(BAR_CONS, BM_CONS);
+          cons_sync();
         }
         if (tid == 0) sc->n_alive = running;
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
       const int n_alive = sc->n_alive;
       const int n_sel = n_alive < W ? n_alive : W;
-      // ---- phase 4c: exact rank among the alive; the W best go to sel[rank]
-      for (int i = tid; i < n_alive; i += BM_CONS) {
-        const double mine = ascore[i];
+      // ---- phase 4c: the W best alive entries go to sel[rank].
+      // More than W alive (flat posteriors): first cut down to exactly W with a 256-bucket histogram
+      // over [cutoff, max] -- everything in buckets above the boundary bucket is in, the boundary
+      // bucket is resolved by exact rank among its few members -- then rank only those W.
+      // Same ordering rule as a full rank count (score desc, candidate index asc), so same result.
+      const double* rs = ascore;  // entries to rank: (rs[i], ri[i]), i < n_rank
+      const int* ri = aidx;
+      int n_rank = n_alive;
+      if (n_alive > W) {
+        for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
+        if (tid == 0) sc->n_b = 0;
+        cons_sync();
+        const double top = cutoff - (double)P.prune;
+        const double scale = P.prune < 0.f ? 256.0 / -(double)P.prune : 0.0;
+        for (int i = tid; i < n_alive; i += BM_CONS) {
+          int b = (int)((top - ascore[i]) * scale);
+          b = b < 0 ? 0 : (b > 255 ? 255 : b);
+          abkt[i] = b;
+          atomicAdd(&hist[b], 1);
+        }
+        cons_sync();
+        if (warp == 0) {  // boundary bucket: first one where the running count reaches W
+          int c[8], tot = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
+          int incl = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+          }
+          int run = incl - tot;  // entries in buckets before my 8
+          if (run < W && incl >= W) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (run < W && run + c[k] >= W) { sc->beta = lane * 8 + k; sc->c0 = run; }
+              run += c[k];
+            }
+          }
+        }
+        cons_sync();
+        const int beta = sc->beta, need = W - sc->c0;
+        for (int i = tid; i < n_alive; i += BM_CONS)
+          if (abkt[i] == beta) blist[atomicAdd(&sc->n_b, 1)] = i;
+        cons_sync();
+        const int m = sc->n_b;
+        for (int t = tid; t < m; t += BM_CONS) {
+          const int i = blist[t];
+          const double mine = ascore[i];
+          int rk = 0;
+          for (int u = 0; u < m; ++u) {
+            const int j = blist[u];
+            const double o = ascore[j];
+            rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
+          }
+          abkt[i] = rk < need ? -1 : 256;  // in / out
+        }
+        cons_sync();
+        // compact the W survivors, alive order preserved
+        {
+          int running = 0;
+          for (int base_i = 0; base_i < n_alive; base_i += BM_CONS) {
+            const int i = base_i + tid;
+            const bool in = i < n_alive && abkt[i] < beta;
+            const unsigned mk = __ballot_sync(FULL, in);
+            if (lane == 0) sc->wcnt[warp] = __popc(mk);
+            cons_sync();
+            int off = running, totc = 0;
+#pragma unroll
+            for (int w = 0; w < BM_CONS / 32; ++w) {
+              const int cw = sc->wcnt[w];
+              if (w < warp) off += cw;
+              totc += cw;
+            }
+            if (in) {
+              const int pos = off + __popc(mk & ((1u << lane) - 1u));
+              bscore[pos] = ascore[i];
+              bidx[pos] = aidx[i];
+            }
+            running += totc;
+            cons_sync();
+          }
+          SSD_ASSERT(running == W);
+        }
+        rs = bscore;
+        ri = bidx;
+        n_rank = W;
+      }
+      for (int i = tid; i < n_rank; i += BM_CONS) {
+        const double mine = rs[i];
         int rk = 0;
-        for (int j = 0; j < n_alive; ++j) {
-          const double o = ascore[j];
+        for (int j = 0; j < n_rank; ++j) {
+          const double o = rs[j];
           rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
         }
-        if (rk < W) sel[rk] = aidx[i];
+        if (rk < W) sel[rk] = ri[i];
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 5: history keys, then keep the best entry per key
       for (int r = tid; r < n_sel; r += BM_CONS) {
@@ -609,7 +713,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         sel_lc[r] = lc;
       }
       for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
         const uint64_t hk = sel_hk[r];
         const int lc = sel_lc[r];
@@ -626,7 +730,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
           sel_keep[r] = keep;
         }
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 6a: slots.  warp 0 scans surviving old prefixes, warp 1 the new ones.
       if (warp == 0) {
@@ -639,7 +743,8 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
           carry += __popc(m);
         }
         if (lane == 0) sc->n_keep_old = carry;
-      } else if (warp == 1) {
+      }
+      if (warp == (BM_CONS > 32 ? 1 : 0)) {
         int carry = 0;
         for (int i0 = 0; i0 < n_sel; i0 += 32) {
           const int i = i0 + lane;
@@ -651,7 +756,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
         if (lane == 0) sc->n_new = carry;
       }
       for (int i = tid; i < TS; i += BM_CONS) tkeys[i] = 0ull;
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
 
       // ---- phase 6b: write the next generation and its hash table
       const int n_old = sc->n_keep_old, n_new = sc->n_new;
@@ -699,7 +804,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
       const Prefix& A = gen[g];
       const int np = sc->np;
       for (int p = tid; p < np; p += BM_CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
       for (int p = tid; p < np; p += BM_CONS) {
         // group = prefixes with equal text after dropping a trailing space
         const uint64_t hs = A.Hstrip[p];
@@ -712,7 +817,7 @@ __global__ void __launch_bounds__(BM_THREADS) beam_kernel(const BeamParams P) {
           }
         newb[p] = (rep == p) ? f : neg_inf();  // one representative per group competes
       }
-      bar_sync(BAR_CONS, BM_CONS);
+      cons_sync();
       if (tid == 0) {
         int best = 0;
         for (int p = 1; p < np; ++p)
@@ -764,7 +869,7 @@ static int beam_max_grid() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms * 8;
+  return sms * 12;
 #endif
 }
 

@@ -71,20 +71,45 @@ __global__ void __launch_bounds__(GR_THREADS) greedy_kernel(const float* __restr
       __syncthreads();
     }
 
-    // ---- argmax of my frame, first maximum wins
+    // ---- argmax of my frame, first maximum wins.  Two passes over my row in shared memory: the
+    // maximum (one FMNMX per element), then the lowest index attaining it.  Rows are V*4 bytes apart,
+    // so each lane starts at a different 16-byte chunk to spread the banks.
     int best_i = -1;
     if (tid < rows) {
-      const float* row = tile + tid * V;
-      float best = 0.f;
-      int v = tid % V;
-      for (int j = 0; j < V; ++j) {
-        float x = row[v];
-        if (v == blank) x = x + bias;
-        if (best_i < 0 || x > best || (x == best && v < best_i)) {
-          best = x;
-          best_i = v;
+      float* row = tile + tid * V;
+      if (bias != 0.f && blank >= 0 && blank < V) row[blank] += bias;  // my own row: no hazard
+      if ((V & 3) == 0) {
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        const int V4 = V >> 2;
+        int c = tid % V4;
+        float m = -INFINITY;
+        for (int j = 0; j < V4; ++j) {
+          const float4 x = row4[c];
+          m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+          c = (c + 1 == V4) ? 0 : c + 1;
         }
-        v = (v + 1 == V) ? 0 : v + 1;
+        int bi = 0x7fffffff;
+        for (int j = 0; j < V4; ++j) {
+          const float4 x = row4[c];
+          const int i0 = 4 * c;
+          // highest index first so that the lowest matching one is what remains
+          int k = x.w == m ? i0 + 3 : 0x7fffffff;
+          k = x.z == m ? i0 + 2 : k;
+          k = x.y == m ? i0 + 1 : k;
+          k = x.x == m ? i0 : k;
+          bi = k < bi ? k : bi;
+          c = (c + 1 == V4) ? 0 : c + 1;
+        }
+        best_i = bi == 0x7fffffff ? 0 : bi;  // all-NaN row: index 0
+      } else {
+        float best = 0.f;
+        for (int v = 0; v < V; ++v) {
+          const float x = row[v];
+          if (best_i < 0 || x > best) {
+            best = x;
+            best_i = v;
+          }
+        }
       }
     }
     // ---- previous frame's argmax

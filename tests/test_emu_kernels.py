@@ -1,0 +1,95 @@
+"""CPU tier: the kernel SOURCES, compiled by g++ against the SIMT emulator (tests/emu/), against the
+oracle on small cases.  Checks kernel logic (barriers, mbarrier pipelines, index arithmetic) without a
+GPU; the product never loads this build.  Also run under reversed / random thread schedules, which is
+what exposes missing barriers."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beam as ob
+from oracle import ctc_loss as ol
+from oracle import greedy as og
+from silent_speech_decoder_b200 import synth
+from silent_speech_decoder_b200.data.vocab import Vocab
+from tests.emu import harness
+
+V = Vocab.default()
+SPACE = V.token_to_id[" "]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return harness.library()
+
+
+def test_greedy(lib, golden_dir):
+    z = np.load(os.path.join(golden_dir, "greedy_ref.npz"))
+    assert harness.greedy(lib, z["kat.lp"], [5, 5], 0) == [[1, 2], [1, 2]]
+    for gen, B, T, bias in (("peaked", 4, 300, 0.0), ("flat", 3, 130, 0.5)):
+        x = getattr(synth, gen)(B, T, 3 + T).numpy()
+        ln = [T, T - 1, T // 2, 0][:B]
+        assert harness.greedy(lib, x, ln, 1, bias) == og.greedy_ids(x, ln, 1, bias)
+
+
+@pytest.mark.parametrize("name", ["peaked50", "flat50", "flat20_bias", "flat1", "flat200"])
+def test_beam_frozen(lib, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "beam_restatement.npz"))
+    width, prune, bias = z[f"{name}.cfg"]
+    ids, score = harness.beam(lib, z[f"{name}.lp"], z[f"{name}.len"], V.blank_id, V.pad_id, SPACE, int(width), float(prune), float(bias))
+    text = ["".join(ob.UNK_GLYPH if i == V.unk_id else V.tokens[i] for i in s) for s in ids]
+    assert text == list(z[f"{name}.text"])
+    assert np.abs(score - z[f"{name}.score"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["flat_edges", "peaked", "test_models_shape", "tight"])
+def test_loss_golden(lib, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "loss_ref.npz"))
+    c = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(name + ".")}
+    nll, grad = harness.loss(lib, c["lp"], c["il"], c["tg"], c["tl"], int(c["blank"]), True, mean_den=c["lp"].shape[0])
+    np.testing.assert_allclose(nll, c["nll64"], rtol=1e-5, atol=1e-6)
+    assert np.abs(grad - c["grad64"]).max() <= 1e-5 * np.abs(c["grad64"]).max() + 1e-12
+    fwd, none = harness.loss(lib, c["lp"], c["il"], c["tg"], c["tl"], int(c["blank"]), True, want_grad=False)
+    assert none is None
+    np.testing.assert_allclose(fwd, c["nll64"], rtol=1e-5, atol=1e-6)
+
+
+def test_loss_wide_lattice_and_extreme_range(lib):
+    # NC=20 code path, and a peaked input against unrelated targets (cells thousands of binades apart)
+    for lp, il, S in ((synth.flat(1, 300, 17), [300], 290), (synth.peaked(1, 600, 77, boost=10.0), [600], 120)):
+        tg, tl = synth.targets(1, S, 18)
+        tl[:] = S
+        nll, grad = harness.loss(lib, lp.numpy(), il, tg.numpy(), tl.numpy(), 1, True, mean_den=1)
+        n64, _, g64 = ol.torch_ctc(lp, torch.tensor(il), tg, tl, 1, True, torch.float64)
+        np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+        assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
+
+
+@pytest.mark.parametrize("order", ["rev", "rnd:3", "rnd:8"])
+def test_schedule_independence(order):
+    """Same results when the emulator visits threads in another order (separate process: the
+    order is read at launch time)."""
+    code = (
+        "import numpy as np, os\n"
+        "from tests.emu import harness\n"
+        "from silent_speech_decoder_b200 import synth\n"
+        "lib = harness.library()\n"
+        "z = np.load('tests/golden/loss_ref.npz')\n"
+        "c = {k.split('.',1)[1]: z[k] for k in z.files if k.startswith('flat_edges.')}\n"
+        "nll, g = harness.loss(lib, c['lp'], c['il'], c['tg'], c['tl'], 1, True, mean_den=6)\n"
+        "assert np.abs(g - c['grad64']).max() <= 1e-5 * np.abs(c['grad64']).max()\n"
+        "x = synth.flat(2, 40, 2205).numpy()\n"
+        "ids, sc = harness.beam(lib, x, [40, 33], 1, 0, 3, 50, -10.0)\n"
+        "print(ids, [round(float(s), 6) for s in sc])\n"
+    )
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for o in ("fwd", order):
+        r = subprocess.run([sys.executable, "-c", code], cwd=repo, env={**os.environ, "SSD_EMU_ORDER": o, "PYTHONPATH": repo},
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1]
