@@ -101,6 +101,13 @@ int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
  *                  grad_output), or NULL for 1
  */
 size_t ssd_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+/* Two kernels serve this entry point: an fp32 fast path that checks its own result per utterance
+ * (posterior mass conservation, range flags) and the exact fp64 path, which recomputes whatever
+ * the fast path flagged and serves the shapes it does not cover (S_max > 255).  After a call,
+ * the uint32 at byte offset ssd_ctc_loss_fallback_counter_offset(...) of the workspace holds how
+ * many utterances took the exact path; the offset is (size_t)-1 when the fast path does not
+ * apply to the shape (everything is exact then). */
+size_t ssd_ctc_loss_fallback_counter_offset(int64_t B, int64_t T, int64_t V, int64_t S_max);
 int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
                  const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
                  const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,

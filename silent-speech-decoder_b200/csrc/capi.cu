@@ -61,6 +61,11 @@ size_t ssd_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_m
   return loss_workspace_bytes(B, T, V, S_max);
 }
 
+size_t ssd_ctc_loss_fallback_counter_offset(int64_t B, int64_t T, int64_t V, int64_t S_max) {
+  if (B <= 0 || T < 0 || V <= 0 || S_max < 0) return (size_t)-1;
+  return loss_fallback_counter_offset(B, T, V, S_max);
+}
+
 int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
                  const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
                  const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,

@@ -111,6 +111,9 @@ struct LossParams {
   int use_tma;
   long long* tlog;  // timeline log (SSD_LOSS_DBG & 8): [role 4][half 2][512][2] clock64 stamps of CTA 0's first utterance
   int dbg;     // timing experiments only (SSD_LOSS_DBG): 1 G idles, 2 M skips staging, 4 H skips recompute
+  // second pass after the fp32 fast path (ctc_loss_fast.cu): only utterances with only[b] != 0 are computed
+  const int* only;
+  const unsigned* only_count;
 };
 
 struct LossSmem {  // byte offsets into dynamic shared memory, identical on host and device
@@ -757,11 +760,14 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
 
   unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
   unsigned qbase = 0u, jbase = 0u, uiter = 0u;
+  if (P.only && *P.only_count == 0u) return;  // nothing was flagged by the fast path
 
   for (;; ++uiter) {
     // ---------------- next utterance + its label tables
     if (tid == 0) {
-      const int u = (int)atomicAdd(P.counter, 1u);
+      int u = (int)atomicAdd(P.counter, 1u);
+      if (P.only)
+        while (u < P.B && P.only[P.order ? P.order[u] : u] == 0) u = (int)atomicAdd(P.counter, 1u);
       sc->utt = u;
       if (u < P.B) {
         const int b = P.order ? P.order[u] : u;
@@ -913,9 +919,27 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
   return true;
 }
 
+// fp32 fast path (ctc_loss_fast.cu)
+size_t loss_fast_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
+                     int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
+                     int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
+                     size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream);
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// workspace = [exact path | fast path]
 size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
   LossPlan pl;
-  return plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 256;
+  const size_t exact = plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 256;
+  return align256(exact) + loss_fast_workspace_bytes(B, T, V, S_max);
+}
+
+size_t loss_fallback_counter_offset(int64_t B, int64_t T, int64_t V, int64_t S_max) {
+  if (!loss_fast_workspace_bytes(B, T, V, S_max)) return (size_t)-1;
+  LossPlan pl;
+  const size_t exact = plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 256;
+  return align256(exact) + 4;  // FastParams::counter[1]
 }
 
 template <int NC, int MINB>
@@ -942,7 +966,24 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   if (!plan_for(B, T, V, S_max, pl))
     return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_loss: no shared-memory plan for V=%lld S_max=%lld", (long long)V, (long long)S_max);
   if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
+  // fp32 fast path first; whatever it flags (and everything it does not cover) is done by the fp64 kernel below
+  const int* only = nullptr;
+  const unsigned* only_count = nullptr;
+  {
+    const size_t fast_off = align256(pl.ws_bytes);
+    const size_t fast_need = loss_fast_workspace_bytes(B, T, V, S_max);
+    if (fast_need) {
+      if (ws_bytes < fast_off + fast_need)
+        return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, fast_off + fast_need);
+      const int rc = loss_fast_launch(lp, B, T, V, sb, st, targets, tgt_stride, S_max, in_len, tg_len, order, blank, zero_inf, mean_den,
+                                      grad_mul, nll, grad, reinterpret_cast<unsigned char*>(ws) + fast_off, fast_need, &only, &only_count,
+                                      stream);
+      if (rc != SSD_OK && rc != SSD_ERR_UNSUPPORTED) return rc;
+      if (rc == SSD_ERR_UNSUPPORTED) only = nullptr, only_count = nullptr;
+    }
+  }
   LossParams P;
+  P.only = only; P.only_count = only_count;
   P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
   P.in_len = in_len; P.tg_len = tg_len; P.order = order;

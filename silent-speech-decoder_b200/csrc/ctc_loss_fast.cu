@@ -1,0 +1,1093 @@
+// CTC loss, forward + backward: the fp32 FAST PATH (nll[B] and d nll / d log_probs in one launch).
+//
+// Replaces torch.nn.CTCLoss as called at reference src/models/losses.py:56 together with ctc_loss.cu,
+// which stays the exact fp64 path: this kernel raises a per-utterance flag whenever fp32 range may not
+// have been enough, and flagged utterances are recomputed by the fp64 kernel (loss_launch, below).
+//
+// Why a second kernel.  ncu showed the fp64 kernel to be bound by its instruction count (240 M
+// warp-instructions at config 2) with the lattice products sitting on the warp that owns the serial
+// chain.  This one keeps the serial chains bare and moves everything else to block-parallel workers:
+//
+//   MF / MB   main sweeps (1 warp each): alpha over frames 0..T-1, beta over T-1..0, concurrently.
+//             A lane owns NC consecutive lattice cells in registers (block floating point: fp32
+//             values + one integer exponent per lane).  Every F_K frames (a "block" boundary) the
+//             strip is renormalised by an exact power of two and written to an L2-resident
+//             checkpoint.  Nothing else is on the chain: no products, no stores per frame.
+//   LF / LB   loaders (1 warp each): 1-D TMA bulk copies (cp.async.bulk + mbarrier) of the next
+//             block's log-prob rows, converted to probabilities for their main.
+//   W0..W3    workers: pull blocks, middle first (a block is ready once MF has passed its start and
+//             MB its end).  Per block: re-run beta from its checkpoint backwards over the block's
+//             frames keeping the pre-emission sums in shared memory, re-run alpha forwards from
+//             its checkpoint, multiply (registers), reduce the posteriors per label class (staging is
+//             sorted by class: one warp prefix scan, class sum = difference) and write
+//             scale * (p - posterior).  Blocks are independent, so workers never wait on each other.
+//
+// alpha and beta never reach HBM; traffic = log-probs + gradient + the per-block checkpoints.
+//
+// Range and the flag.  Linear-domain fp32 cannot represent every lattice (cells of one lane may
+// legitimately differ by more than 2^150 when confident posteriors disagree with the target).
+// Instead of proving range a priori the kernel checks the result: any mass lost to underflow in
+// either sweep makes sum_v posterior_t(v) differ between frames, so every frame's sum is compared
+// with 1 (D3).  Together with D1 (a log-prob beyond +-80 or NaN was seen: exp leaves fp32 range), D2 (a strip went
+// non-finite) and D4 (Z not a positive finite number: infeasible or lost) this decides the flag.
+#include <cmath>
+#include <cstdlib>
+
+#include "ssd_common.cuh"
+
+namespace ssd {
+
+constexpr int F_K = 8;          // frames per block = renormalisation and checkpoint interval
+constexpr int F_KS = 9;         // class-row stride of a probability block in floats: odd, so that a warp's gather of 32
+                                // different classes at one frame touches 32 different banks (stride 8 folds them onto 4)
+constexpr int F_THREADS = 256;  // MF MB LF LB + 4 workers
+constexpr int F_W = 4;
+constexpr int F_NP = 3;    // probability-row ring depth per main (blocks)
+constexpr int F_NRAW = 3;  // raw-row ring depth per main
+constexpr int F_TOP = 40;  // renormalised strips have their largest cell in [2^40, 2^41)
+constexpr int F_SPAD = 256;  // label staging capacity (S <= 255 on this path)
+constexpr float F_MASS_TOL = 1.5e-5f;
+constexpr float F_LP_ABS = 80.f;  // log-probs beyond +-80 (or NaN) send the utterance to the exact path
+
+// ------------------------------------------------------------------ scalar helpers
+// 2^d for d in [-126, 127]; zero below, 2^127 above
+__device__ __forceinline__ float pow2c(int d) {
+  d = d > 127 ? 127 : d;
+  return d < -126 ? 0.f : __int_as_float((d + 127) << 23);
+}
+__device__ __forceinline__ int expo_f(float v) { return ((__float_as_int(v) >> 23) & 0xff) - 127; }
+__device__ __forceinline__ float ex2_approx(float x) {
+#ifdef SSD_EMU
+  return exp2f(x);
+#else
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
+}
+// exp(lp), branch free and with ONE slow-pipe instruction (MUFU.EX2): round-to-nearest by the magic-number
+// add, the argument split so that its rounding does not scale with |lp|, the integer part added straight
+// into the exponent field.  Inputs outside +-F_LP_ABS (flagged by the caller, D1) give a harmless finite value.
+__device__ __forceinline__ float prob_f(float lp) {
+  const float MAGIC = 12582912.f;  // 1.5 * 2^23: t + MAGIC holds rint(t) in its low mantissa bits
+  const float t = fminf(fmaxf(lp * 1.4426950408889634f, -125.f), 125.f);
+  const float kf = t + MAGIC;
+  const float kr = kf - MAGIC;
+  float r = fmaf(lp, 1.4426950216293335f, -kr);  // log2(e) high part
+  r = fmaf(lp, 1.9259629911266175e-8f, r);       // log2(e) low part
+  r = fminf(fmaxf(r, -1.f), 1.f);                // only binds outside the flagged range
+  return __int_as_float(__float_as_int(ex2_approx(r)) + (__float_as_int(kf) << 23));
+}
+__device__ __forceinline__ float ld_cg(const float* p) {
+#ifdef SSD_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ int ld_cg(const int* p) {
+#ifdef SSD_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+
+// Sum over the warp of values in [0, 1.5]: 2^-26 fixed point through the integer reduction unit (one REDUX
+// instead of five dependent shuffle rounds; 32 * 1.5 * 2^26 < 2^32).  A lane holding anything else (NaN, inf,
+// negative, larger) counts as 1.5, which no valid frame can absorb: D3 fires.
+__device__ __forceinline__ float warp_sum_fx(float v) {
+  const bool valid = v >= 0.f && v <= 1.5f;
+  const unsigned q = (unsigned)__float2int_rn((valid ? v : 1.5f) * 67108864.f);
+  return (float)__reduce_add_sync(FULL, q) * (1.f / 67108864.f);
+}
+
+struct FastParams {
+  const float* lp;
+  int64_t T, sb, st;
+  int B, V;
+  const int64_t* targets;
+  int64_t tgt_stride;
+  int S_max;
+  const int64_t* in_len;
+  const int64_t* tg_len;
+  const int32_t* order;
+  int blank, zero_inf;
+  int64_t mean_den;
+  const float* grad_mul;
+  float* nll;
+  float* grad;
+  unsigned* counter;   // [0] utterance queue, [1] number of flagged utterances
+  unsigned* sm_slot;   // [#SM] arrival counter of CTAs per SM (role rotation, see loss_fast_kernel)
+  int* flags;          // [B] non-zero = recompute on the exact path (1 not covered, 2 D1, 4 D2, 8 D3, 16 D4)
+  unsigned char* ckpt; // per CTA: [2 dirs][nb_max] records
+  size_t ckpt_cta_bytes, ckpt_rec_bytes;
+  int nb_max;
+  int RS;  // worker row stride in floats
+  int use_tma;
+  long long* tlog;  // SSD_LOSS_DBG & 8: [8 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
+};
+constexpr int F_TLOG_N = 256, F_TLOG_S = 6;
+
+__device__ __forceinline__ void fstamp(const FastParams& P, unsigned uiter, int idx, int slot, long long tag = -1) {
+#ifndef SSD_EMU
+  if (P.tlog && blockIdx.x == 0 && uiter == 0 && idx < F_TLOG_N && (threadIdx.x & 31) == 0)
+    P.tlog[(((int)threadIdx.x >> 5) * F_TLOG_N + idx) * F_TLOG_S + slot] = tag >= 0 ? tag : clock64();
+#endif
+}
+
+struct FastSmem {  // byte offsets into dynamic shared memory, identical on host and device
+  size_t p_slot, raw_slot, main_bytes, wrow_bytes, worker_bytes;
+  size_t main_off, worker_off, lab_off, pos_off, cls_off, tab_off, bar_off, blk_off, scal_off, total;
+};
+
+// mbarrier indices: per main F_NP full + F_NP empty + F_NRAW raw; then z_ready; then 2 raw barriers per worker
+constexpr int FB_PFULL = 0, FB_PEMPTY = F_NP, FB_RAW = 2 * F_NP, FB_PER_MAIN = 2 * F_NP + F_NRAW;
+constexpr int FB_Z = 2 * FB_PER_MAIN, FB_WRAW = FB_Z + 1, FB_TOTAL = FB_WRAW + 2 * F_W;
+
+// Probability blocks are stored class-major: p[v * F_KS + r] for the block's frame r (row V is the all-zero dummy
+// class of out-of-lattice cells).  A lane's label column is then ONE pointer for the whole block and a frame is
+// an immediate offset from it.
+__host__ __device__ inline FastSmem fast_smem_layout(int V, int RS, int S_tab, int nb_max) {
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  FastSmem m;
+  m.p_slot = al((size_t)(V + 1) * F_KS * 4 + 16);
+  m.raw_slot = al((size_t)F_K * V * 4);
+  m.main_bytes = F_NP * m.p_slot + F_NRAW * m.raw_slot;
+  m.wrow_bytes = al((size_t)F_K * RS * 4);
+  m.worker_bytes = m.wrow_bytes + m.p_slot + 2 * m.raw_slot;
+  size_t o = 0;
+  m.main_off = o; o += 2 * m.main_bytes;
+  m.worker_off = o; o += F_W * m.worker_bytes;
+  m.lab_off = o; o += al((size_t)S_tab * 4);
+  m.pos_off = o; o += al((size_t)S_tab * 4);
+  m.cls_off = o; o += al((size_t)(V + 2) * 4);
+  m.tab_off = o; o += 4 * 16 * 32 * 4;  // per-lane label tables, see build_lane_tables
+  m.bar_off = o; o += al((size_t)FB_TOTAL * 8);
+  m.blk_off = o; o += al((size_t)nb_max * 8);
+  m.scal_off = o; o += 128;
+  m.total = o;
+  return m;
+}
+
+struct FastScal {
+  int utt, b, T, S, skip;
+  float scale;
+  int next_blk;    // worker block queue
+  int uflag;       // this utterance needs the exact path (reason bits)
+  float inv_zm;    // 1 / mantissa of Z
+  int ez;          // exponent of Z
+  int rot;         // role rotation of this CTA (0/1)
+};
+
+// ------------------------------------------------------------------ strips
+// Strip of NC cells per lane (cell = lane*NC + i, even i = blank), true value = x[i] * 2^e.
+template <int NC>
+struct FStrip {
+  float x[NC];
+  float fin;  // 2^(neighbour e - my e): brings the neighbour's boundary cells into my basis
+  int e;
+};
+
+// per-lane label tables of one sweep direction: offset of every label cell's class in a probability
+// block, 0/1 skip multipliers, optionally the class-sorted staging slot
+template <int NC>
+struct FLabels {
+  int off[NC / 2];
+  float skf[NC / 2];
+};
+
+// The tables are the same for every warp of the CTA: built once per utterance into shared memory as
+// [4][NC/2][32] (class offset | alpha skip | beta skip | class-sorted staging slot), one entry per thread,
+// and read by each role when (and only while) it needs them.
+template <int NC>
+__device__ __forceinline__ void build_lane_tables(int S, int V, const int* __restrict__ lab, const int* __restrict__ pos, int* tab) {
+  const int t = (int)threadIdx.x;
+  if (t >= (NC / 2) * 32) return;
+  const int k = t >> 5, lane = t & 31;
+  const int L = 2 * S + 1;
+  const int c = lane * NC + 2 * k + 1;  // odd cell
+  int col = V;                          // dummy class (p = 0) outside the lattice
+  float ska = 0.f, skb = 0.f;
+  int sp = -1;
+  if (c < L) {
+    const int j = (c - 1) >> 1;
+    col = lab[j];
+    sp = pos[j];
+    if (c >= 3 && lab[j - 1] != col) ska = 1.f;
+    if (c + 2 < L && lab[j + 1] != col) skb = 1.f;
+  }
+  constexpr int N = (NC / 2) * 32;
+  tab[t] = col * F_KS * 4;  // byte offset of the class row in a probability block
+  tab[N + t] = __float_as_int(ska);
+  tab[2 * N + t] = __float_as_int(skb);
+  tab[3 * N + t] = sp;
+}
+template <int NC, int DIR>
+__device__ __forceinline__ void load_labels(FLabels<NC>& lt, const int* __restrict__ tab) {
+  const int lane = lane_id();
+  constexpr int N = (NC / 2) * 32;
+#pragma unroll
+  for (int k = 0; k < NC / 2; ++k) {
+    lt.off[k] = tab[k * 32 + lane];
+    lt.skf[k] = __int_as_float(tab[(DIR ? 2 : 1) * N + k * 32 + lane]);
+  }
+}
+
+template <int NC>
+struct FProbs {  // one frame
+  float lab[NC / 2];
+  float blank;
+};
+// Frame iteration over a class-major block.  Each label cell keeps ONE byte pointer into the block (its class
+// row); a frame is that pointer plus an immediate, so a step costs no address arithmetic.  Two frames per
+// trip with alternating register sets: the next frame's probabilities are always in flight during a step and
+// never copied.  body(r, probs) is called for the block's frames in sweep order.
+#ifdef SSD_EMU
+typedef const char* saddr_t;
+__device__ __forceinline__ saddr_t saddr_of(const void* p) { return reinterpret_cast<const char*>(p); }
+template <int IMM>
+__device__ __forceinline__ float lds_pinned(saddr_t a) { return *reinterpret_cast<const float*>(a + IMM); }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t saddr_of(const void* p) { return smem_u32(p); }
+// volatile: the compiler may not sink the load into the branch that consumes it, which is what keeps the
+// next frame's probabilities in flight one whole step ahead
+template <int IMM>
+__device__ __forceinline__ float lds_pinned(saddr_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(IMM));
+  return v;
+}
+#endif
+template <int NC>
+struct PPtr {
+  saddr_t lab[NC / 2];
+  saddr_t blank;
+};
+template <int NC, int IMM>
+__device__ __forceinline__ void load_probs(FProbs<NC>& p, const PPtr<NC>& pp) {
+  p.blank = lds_pinned<IMM>(pp.blank);
+#pragma unroll
+  for (int k = 0; k < NC / 2; ++k) p.lab[k] = lds_pinned<IMM>(pp.lab[k]);
+}
+template <int NC, int DIR, class F>
+__device__ __forceinline__ void for_frames(const float* pblk, int n, const FLabels<NC>& lt, int blank_off, F&& body) {
+  constexpr int D = DIR ? -4 : 4;
+  const saddr_t base = saddr_of(pblk) + (DIR ? (n - 1) * 4 : 0);
+  PPtr<NC> pp;
+  pp.blank = base + blank_off;
+#pragma unroll
+  for (int k = 0; k < NC / 2; ++k) pp.lab[k] = base + lt.off[k];
+  FProbs<NC> A, B;
+  load_probs<NC, 0>(A, pp);
+#pragma unroll 1
+  for (int rr = 0; rr < n; rr += 2) {
+    const int r = DIR ? n - 1 - rr : rr;
+    const bool two = rr + 1 < n;
+    if (two) load_probs<NC, D>(B, pp);
+    body(r, A);
+    if (two) {
+      if (rr + 2 < n) {
+        pp.blank += 2 * D;
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) pp.lab[k] += 2 * D;
+        load_probs<NC, 0>(A, pp);
+      }
+      body(DIR ? r - 1 : r + 1, B);
+    }
+  }
+}
+
+// One frame of the recursion.  DIR 0 (alpha): cell s pulls from s-1 and, label cells with a different
+// label two back, s-2.  DIR 1 (beta): the mirror image, from s+1 and s+2.  SUMS: also return the
+// pre-emission sums (what the posterior needs from the beta side).
+//
+// The neighbour lane's boundary cells arrive by shuffle.  A shuffle costs an in-order warp ~25 cycles twice
+// (result latency, and the source register may not be overwritten before it is read), so they are
+// software-pipelined: a step first computes the cells the NEXT step's shuffle reads, issues that shuffle,
+// and only touches the values shuffled one step earlier (`in`) at its very end.
+struct Inflow {
+  float a, b;  // neighbour's boundary cells in ITS basis (b: beta only)
+};
+template <int NC, int DIR>
+__device__ __forceinline__ void inflow_prime(const FStrip<NC>& s, Inflow& in) {
+  if (DIR == 0) {
+    in.a = __shfl_up_sync(FULL, s.x[NC - 1], 1);
+    in.b = 0.f;
+  } else {
+    in.a = __shfl_down_sync(FULL, s.x[0], 1);
+    in.b = __shfl_down_sync(FULL, s.x[1], 1);
+  }
+}
+template <int NC, int DIR, bool SUMS>
+__device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<NC>& lt, const FProbs<NC>& p, float* sums) {
+  float (&x)[NC] = s.x;
+  Inflow nxt;
+  auto cell = [&](int i, float a1, float a2) {
+    float sum = x[i] + a1;
+    if (i & 1) {
+      sum = fmaf(lt.skf[i >> 1], a2, sum);
+      if (SUMS) sums[i] = sum;
+      x[i] = sum * p.lab[i >> 1];
+    } else {
+      if (SUMS) sums[i] = sum;
+      x[i] = sum * p.blank;
+    }
+  };
+  if (DIR == 0) {
+    // descending: inputs of lower cells are still intact
+    cell(NC - 1, x[NC - 2], x[NC - 3]);
+    nxt.a = __shfl_up_sync(FULL, x[NC - 1], 1);
+    nxt.b = 0.f;
+#pragma unroll
+    for (int i = NC - 2; i >= 2; --i) cell(i, x[i - 1], x[i - 2]);
+    const float n1 = in.a * s.fin;  // lane 0: fin = 0
+    cell(1, x[0], n1);
+    cell(0, n1, 0.f);
+  } else {
+    // ascending
+    cell(0, x[1], 0.f);
+    cell(1, x[2], x[3]);
+    nxt.a = __shfl_down_sync(FULL, x[0], 1);
+    nxt.b = __shfl_down_sync(FULL, x[1], 1);
+#pragma unroll
+    for (int i = 2; i < NC - 1; ++i) cell(i, x[i + 1], x[i + 2 < NC ? i + 2 : NC - 1]);
+    const float m0 = in.a * s.fin, m1 = in.b * s.fin;  // lane 31: fin = 0
+    cell(NC - 1, m0, m1);
+  }
+  in = nxt;
+}
+
+// the boundary factor both the mains and the workers derive from the lane exponents
+template <int DIR>
+__device__ __forceinline__ float fin_of(int e_me) {
+  const int lane = lane_id();
+  const int e_nb = DIR == 0 ? __shfl_up_sync(FULL, e_me, 1) : __shfl_down_sync(FULL, e_me, 1);
+  const bool edge = DIR == 0 ? lane == 0 : lane == 31;
+  return edge ? 0.f : pow2c(e_nb - e_me);
+}
+
+// Block boundary: bring my largest cell to [2^TOP, 2^(TOP+1)), agree on exponents with the
+// neighbour the mass comes from.  Returns false if the strip is not finite (D2).
+template <int NC, int DIR>
+__device__ __forceinline__ bool renorm_exchange(FStrip<NC>& s) {
+  const int lane = lane_id();
+  float m = s.x[0];
+#pragma unroll
+  for (int i = 1; i < NC; ++i) m = fmaxf(m, s.x[i]);
+  const bool ok = m < 3.0e38f;              // false for inf; NaN cells surface through D3/D4
+  const bool live = m >= 1.17549435e-38f;   // below the normal range: treat as empty
+  int k = expo_f(m) - F_TOP;
+  k = k < -120 ? -120 : k;
+  k = live ? k : 0;
+  const float f = live ? pow2c(-k) : 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s.x[i] *= f;
+  s.e += k;
+  // an empty strip takes the exponent of the nearest live strip on the side its mass will come from
+  const unsigned lv = __ballot_sync(FULL, live);
+  int src;
+  if (DIR == 0) {
+    const unsigned below = lv & ((1u << lane) - 1u);
+    src = below ? 31 - __clz((int)below) : lane;
+  } else {
+    const unsigned above = lane == 31 ? 0u : (lv >> (lane + 1)) << (lane + 1);
+    src = above ? __ffs((int)above) - 1 : lane;
+  }
+  const int e_near = __shfl_sync(FULL, s.e, src);
+  if (!live) s.e = e_near;
+  // a live neighbour that dwarfs me: rebase on it so that its boundary cells stay representable
+  const int e_nb = DIR == 0 ? __shfl_up_sync(FULL, s.e, 1) : __shfl_down_sync(FULL, s.e, 1);
+  const int nb = DIR == 0 ? lane - 1 : lane + 1;
+  const bool nb_live = nb >= 0 && nb < 32 && ((lv >> (nb & 31)) & 1u);
+  const int d = e_nb - s.e;
+  if (nb_live && d > 100) {
+    const float g = pow2c(-d);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) s.x[i] *= g;
+    s.e = e_nb;
+  }
+  s.fin = fin_of<DIR>(s.e);
+  return ok;
+}
+
+template <int NC, int DIR>
+__device__ __forceinline__ void sweep_init_f(int L, FStrip<NC>& s) {
+  const int lane = lane_id();
+  const int c0 = DIR ? L - 1 : 0;  // the virtual frame before the first one holds all mass in one cell
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s.x[i] = (lane * NC + i == c0) ? 1.f : 0.f;
+  s.e = 0;
+  s.fin = (DIR == 0 ? lane == 0 : lane == 31) ? 0.f : 1.f;
+}
+
+// checkpoint record: [NC][32] cells, [32] exponents; lanes beyond the lattice hold zeros and are skipped
+template <int NC>
+__device__ __forceinline__ void ckpt_store(unsigned char* rec, const FStrip<NC>& s, int L) {
+  const int lane = lane_id();
+  float* cx = reinterpret_cast<float*>(rec);
+  if (lane * NC < L) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) cx[i * 32 + lane] = s.x[i];
+  }
+  reinterpret_cast<int*>(cx + NC * 32)[lane] = s.e;
+}
+template <int NC>
+__device__ __forceinline__ void ckpt_load(const unsigned char* rec, FStrip<NC>& s, int L) {
+  const int lane = lane_id();
+  const float* cx = reinterpret_cast<const float*>(rec);
+  const bool in = lane * NC < L;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s.x[i] = in ? ld_cg(cx + i * 32 + lane) : 0.f;
+  s.e = ld_cg(reinterpret_cast<const int*>(cx + NC * 32) + lane);
+}
+
+struct FPlan {  // per utterance
+  int b, Tb, S, L, NB;
+};
+
+// i-th block in (approximate) order of readiness.  Block q is ready at step max(q*K, Tb - (q+1)*K): two
+// arithmetic sequences with the same stride that meet at qc, so walking outwards from qc alternately
+// visits them in order; whichever side runs out first leaves the rest to the other.
+__device__ __forceinline__ int block_order(int i, int NB, int Tb) {
+  int qc = (Tb - F_K + 2 * F_K - 1) / (2 * F_K);  // first block whose readiness is set by the forward sweep
+  qc = qc < 0 ? 0 : (qc > NB - 1 ? NB - 1 : qc);
+  const int nhi = NB - qc, nlo = qc;
+  const int m = nhi < nlo ? nhi : nlo;
+  if (i < 2 * m) return (i & 1) ? qc - 1 - (i >> 1) : qc + (i >> 1);
+  return nhi > nlo ? qc + (i - m) : qc - 1 - (i - m);
+}
+
+// Convert one block of raw log-prob rows into a class-major probability block.  `raw` is the block in
+// shared memory ([n][V], TMA-loaded) or, if null, `graw` the same rows in global memory (row stride st).
+// Two (frame quad, class) items per lane and pass: eight independent load -> exp chains in flight.
+// Returns non-zero if a value outside +-F_LP_ABS (or NaN) was seen (D1).
+template <bool SMEM>
+__device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
+                                               float* __restrict__ pblk) {
+  const int lane = lane_id();
+  int bad = 0;
+  for (int base = 0; base < 2 * V; base += 64) {
+    float lp[2][4];
+    int vv[2], hh[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      int idx = base + 32 * u + lane;  // consecutive lanes, consecutive classes
+      idx = idx < 2 * V ? idx : 2 * V - 1;
+      hh[u] = idx >= V ? 1 : 0;
+      vv[u] = idx - hh[u] * V;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int r = hh[u] * 4 + j;
+        r = r < n ? r : n - 1;  // rows beyond a partial block: re-read the last one, masked below
+        lp[u][j] = SMEM ? raw[r * V + vv[u]] : ld_stream(graw + (int64_t)r * st + vv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float pr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bad |= !(fabsf(lp[u][j]) <= F_LP_ABS);
+        const float pv = prob_f(lp[u][j]);
+        pr[j] = hh[u] * 4 + j < n ? pv : 0.f;
+      }
+      if (base + 32 * u + lane < 2 * V) {
+        float* dst = pblk + vv[u] * F_KS + hh[u] * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = pr[j];
+      }
+    }
+  }
+  return bad;
+}
+// one loop per source: the unused path's address arithmetic would otherwise ride along predicated off
+__device__ __forceinline__ int convert_block(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
+                                             float* __restrict__ pblk) {
+  return raw ? convert_block_t<true>(raw, graw, st, n, V, pblk) : convert_block_t<false>(raw, graw, st, n, V, pblk);
+}
+
+struct MainView {  // one main's rings
+  unsigned char* base;
+  uint64_t* bar;
+  size_t p_slot, raw_slot;
+  __device__ __forceinline__ float* p(int slot) const { return reinterpret_cast<float*>(base + slot * p_slot); }
+  __device__ __forceinline__ float* raw(int slot) const { return reinterpret_cast<float*>(base + F_NP * p_slot + slot * raw_slot); }
+};
+
+// ------------------------------------------------------------------ L: loader / converter of one main
+template <int DIR>
+__device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan& pl, unsigned qbase, FastScal* sc, unsigned uiter) {
+  const int lane = lane_id();
+  const int V = P.V;
+  const float* base = P.lp + (int64_t)pl.b * P.sb;
+  auto blk_of = [&](int bi) { return DIR ? pl.NB - 1 - bi : bi; };
+  auto issue_raw = [&](int bi) {  // lane 0
+    const int q = blk_of(bi);
+    const int n = min(F_K, pl.Tb - q * F_K);
+    const int slot = (int)((qbase + (unsigned)bi) % F_NRAW);
+    const uint32_t bytes = (uint32_t)(n * V * 4);
+    mbar_arrive_expect_tx(&mv.bar[FB_RAW + slot], bytes);
+    bulk_g2s(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot]);
+  };
+  if (P.use_tma && lane == 0)
+    for (int bi = 0; bi < pl.NB && bi < F_NRAW - 1; ++bi) issue_raw(bi);
+  int lpbad = 0;
+  for (int bi = 0; bi < pl.NB; ++bi) {
+    __syncwarp();  // every lane is done with raw slot (bi-1) before lane 0 re-arms it
+    if (P.use_tma && lane == 0 && bi + F_NRAW - 1 < pl.NB) issue_raw(bi + F_NRAW - 1);
+    const unsigned Q = qbase + (unsigned)bi;
+    const int slot = (int)(Q % F_NP);
+    fstamp(P, uiter, bi, 0);
+    mbar_wait_relaxed(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u);  // I am blocks ahead: no hurry
+    fstamp(P, uiter, bi, 1);
+    const int q = blk_of(bi);
+    const int n = min(F_K, pl.Tb - q * F_K);
+    const float* raw = nullptr;
+    if (P.use_tma) {
+      const int rs = (int)(Q % F_NRAW);
+      mbar_wait(&mv.bar[FB_RAW + rs], (Q / F_NRAW) & 1u);
+      raw = mv.raw(rs);
+    }
+    fstamp(P, uiter, bi, 2);
+    lpbad |= convert_block(raw, base + (int64_t)q * F_K * P.st, P.st, n, V, mv.p(slot));
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&mv.bar[FB_PFULL + slot]);
+    fstamp(P, uiter, bi, 3);
+  }
+  if (DIR == 0 && __any_sync(FULL, lpbad) && lane == 0) atomicOr(&sc->uflag, 2);  // D1
+}
+
+// ------------------------------------------------------------------ M: main sweep of one direction
+template <int NC, int DIR>
+__device__ void fast_main(const FastParams& P, const MainView& mv, const FPlan& pl, const int* __restrict__ tab, unsigned qbase,
+                          unsigned char* ckpt_cta, uint64_t* blk_ready, FastScal* sc, unsigned uiter) {
+  const int lane = lane_id();
+  const int blank_off = P.blank * F_KS * 4;  // bytes
+  FLabels<NC> lt;
+  load_labels<NC, DIR>(lt, tab);
+  FStrip<NC> s;
+  sweep_init_f<NC, DIR>(pl.L, s);
+  unsigned char* ck = ckpt_cta + (size_t)DIR * P.nb_max * P.ckpt_rec_bytes;
+  // checkpoints: the lanes' stores are ordered before lane 0's (release) arrive by the __syncwarp
+  {  // the start state is the checkpoint of my first block
+    const int q0 = DIR ? pl.NB - 1 : 0;
+    ckpt_store<NC>(ck + (size_t)q0 * P.ckpt_rec_bytes, s, pl.L);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&blk_ready[q0]);
+  }
+  Inflow in;
+  inflow_prime<NC, DIR>(s, in);
+  bool ok = true;
+  for (int bi = 0; bi < pl.NB; ++bi) {
+    const int q = DIR ? pl.NB - 1 - bi : bi;
+    const unsigned Q = qbase + (unsigned)bi;
+    const int slot = (int)(Q % F_NP);
+    fstamp(P, uiter, bi, 0);
+    mbar_wait(&mv.bar[FB_PFULL + slot], (Q / F_NP) & 1u);
+    fstamp(P, uiter, bi, 1);
+    const float* pblk = mv.p(slot);
+    const int n = min(F_K, pl.Tb - q * F_K);
+    for_frames<NC, DIR>(pblk, n, lt, blank_off, [&](int, const FProbs<NC>& pc) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr); });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&mv.bar[FB_PEMPTY + slot]);
+    fstamp(P, uiter, bi, 2);
+    ok &= renorm_exchange<NC, DIR>(s);
+    inflow_prime<NC, DIR>(s, in);  // the values shuffled before the renormalisation are in the old basis
+    const int qn = DIR ? q - 1 : q + 1;  // the block this state starts
+    if (qn >= 0 && qn < pl.NB) {
+      ckpt_store<NC>(ck + (size_t)qn * P.ckpt_rec_bytes, s, pl.L);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&blk_ready[qn]);
+    }
+    fstamp(P, uiter, bi, 3);
+  }
+  if (__any_sync(FULL, !ok) && lane == 0) atomicOr(&sc->uflag, 4);  // D2
+}
+
+// ------------------------------------------------------------------ W: block workers
+struct WorkerView {
+  float* rows;   // [F_K][RS]: beta~ rows, then (same storage) the staged posteriors
+  float* pblk;   // class-major probabilities of the block in flight
+  float* raw0;   // two TMA landing buffers (one block ahead), raw_stride floats apart
+  int raw_stride;
+  uint64_t* rawbar;  // [2]
+};
+
+template <int NC>
+__device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __restrict__ tab,
+                            const int* __restrict__ cls, const WorkerView& wv, const unsigned char* ckpt_cta, uint64_t* blk_ready,
+                            uint64_t* z_ready, unsigned uiter, unsigned& nraw, FastScal* sc) {
+  const int lane = lane_id();
+  const int V = P.V, RS = P.RS, S = pl.S;
+  const int blank_off = P.blank * F_KS * 4;  // bytes
+  const bool want_grad = P.grad != nullptr;
+  float* rows = wv.rows;
+  float* pblk = wv.pblk;
+  const unsigned char* ck_a = ckpt_cta;
+  const unsigned char* ck_b = ckpt_cta + (size_t)P.nb_max * P.ckpt_rec_bytes;
+  const float* lp_base = P.lp + (int64_t)pl.b * P.sb;
+  float* g_base = want_grad ? P.grad + (int64_t)pl.b * P.sb : nullptr;
+  const float scale = sc->scale;
+  bool mass_ok = true;
+  // class passes of the gradient stage: lane handles classes lane, lane+32, ..; per pass the longest class range
+  const int ncls_it = (V + 31) >> 5;  // <= 4 (V <= 128)
+  unsigned mlen = 0u;
+  for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
+    const int len = v < V ? cls[v + 1] - cls[v] : 0;
+    mlen |= (unsigned)min(__reduce_max_sync(FULL, len), 255) << (8 * ci);
+  }
+
+  // without a gradient only Z is needed: the first block alone
+  const int nblk = want_grad ? pl.NB : 1;
+  auto grab = [&]() {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&sc->next_blk, 1);
+    return __shfl_sync(FULL, i, 0);
+  };
+  auto issue_raw = [&](int i, unsigned use) {  // lane 0: the block's rows -> landing buffer (use & 1)
+    const int q = block_order(i, pl.NB, pl.Tb);
+    const int n = min(F_K, pl.Tb - q * F_K);
+    const uint32_t bytes = (uint32_t)(n * V * 4);
+    mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes);
+    bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
+  };
+  int i = grab();
+  if (i < nblk && P.use_tma && lane == 0) issue_raw(i, nraw);
+  int nmine = 0;
+  for (; i < nblk; ++nmine) {
+    fstamp(P, uiter, nmine, 0);
+    const int q = block_order(i, pl.NB, pl.Tb);
+    const int t0 = q * F_K;
+    const int n = min(F_K, pl.Tb - t0);
+    // one block ahead: claim the next block and start its copy
+    __syncwarp();  // the landing buffer about to be re-armed was read by all lanes one block ago
+    const int i_next = grab();
+    if (i_next < nblk && P.use_tma && lane == 0) issue_raw(i_next, nraw + 1);
+    // ---- probabilities of the block's frames (own copy: workers run behind the mains' rings)
+    const float* raw = nullptr;
+    if (P.use_tma) {
+      mbar_wait(&wv.rawbar[nraw & 1u], (nraw >> 1) & 1u);
+      raw = wv.raw0 + (nraw & 1u) * wv.raw_stride;
+    }
+    ++nraw;
+    convert_block(raw, lp_base + (int64_t)t0 * P.st, P.st, n, V, pblk);
+    fstamp(P, uiter, nmine, 1);
+    mbar_wait_relaxed(&blk_ready[q], 0u);  // both checkpoints of the block are published
+    fstamp(P, uiter, nmine, 2);
+    fstamp(P, uiter, nmine, 5, q);
+    __syncwarp();
+    // ---- beta backwards over the block: pre-emission sums -> rows
+    FStrip<NC> s;
+    ckpt_load<NC>(ck_b + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
+    const int e_beta = s.e;
+    s.fin = fin_of<1>(s.e);
+    {
+      FLabels<NC> lb;
+      load_labels<NC, 1>(lb, tab);
+      Inflow in;
+      inflow_prime<NC, 1>(s, in);
+      for_frames<NC, 1>(pblk, n, lb, blank_off, [&](int r, const FProbs<NC>& pc) {
+        float sums[NC];
+        fstep<NC, 1, true>(s, in, lb, pc, sums);
+        float2* dst = reinterpret_cast<float2*>(rows + r * RS) + lane;
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) dst[k * 32] = make_float2(sums[2 * k], sums[2 * k + 1]);
+      });
+    }
+    __syncwarp();
+    fstamp(P, uiter, nmine, 3);
+    // ---- alpha forwards
+    ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
+    const int e_alpha = s.e;
+    FLabels<NC> la;
+    load_labels<NC, 0>(la, tab);
+    if (i == 0) {
+      // Z = sum over the lattice of alpha_t * beta~_t at the block's first frame (unscaled pass)
+      FStrip<NC> z = s;
+      z.fin = fin_of<0>(z.e);
+      Inflow zin;
+      inflow_prime<NC, 0>(z, zin);
+      FProbs<NC> pc;
+      pc.blank = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + blank_off);
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) pc.lab[k] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + la.off[k]);
+      fstep<NC, 0, false>(z, zin, la, pc, nullptr);
+      const float2* src = reinterpret_cast<const float2*>(rows) + lane;
+      float sl = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) {
+        const float2 w = src[k * 32];
+        sl = fmaf(z.x[2 * k], w.x, sl);
+        sl = fmaf(z.x[2 * k + 1], w.y, sl);
+      }
+      const bool okl = sl >= 1.17549435e-38f && sl < 3.0e38f;
+      const int q_l = e_alpha + e_beta;
+      const int key = okl ? q_l + expo_f(sl) : -(1 << 30);
+      const int Qm = __reduce_max_sync(FULL, key);
+      const bool bad_lane = !(sl >= 0.f && sl < 3.0e38f);  // NaN / inf somewhere
+      const bool any_bad = __any_sync(FULL, bad_lane);
+      float inv_zm = 0.f;
+      int ez = 0;
+      const bool feasible = Qm > -(1 << 30) && !any_bad;
+      if (feasible) {
+        // every lane's partial in units of 2^Qm: at most 2 each, negligible ones flush
+        float tot = okl ? sl * pow2c(q_l - Qm) : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+        const int et = expo_f(tot);
+        const float zm = tot * pow2c(-et);  // [1,2)
+        inv_zm = 1.f / zm;
+        ez = Qm + et;
+        if (lane == 0) P.nll[pl.b] = (float)(-(log((double)zm) + (double)ez * 0.69314718055994530942));
+      } else if (lane == 0) {
+        atomicOr(&sc->uflag, 16);  // D4: infeasible or lost -- the exact path decides which
+      }
+      if (lane == 0) {
+        sc->inv_zm = inv_zm;
+        sc->ez = ez;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(z_ready);
+    }
+    if (!want_grad) break;
+    mbar_wait_relaxed(z_ready, uiter & 1u);
+    {
+      // run alpha pre-scaled by c = 2^(e_alpha + e_beta - eZ) / Zm: the products below are posteriors
+      const float c = pow2c(e_alpha + e_beta - sc->ez) * sc->inv_zm;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) s.x[k] *= c;
+      // inflow = x_nb * 2^(ea_nb - ea_me) * c_me / c_nb = x_nb * 2^(eb_me - eb_nb)
+      const int eb_nb = __shfl_up_sync(FULL, e_beta, 1);
+      s.fin = lane == 0 ? 0.f : pow2c(e_beta - eb_nb);
+    }
+    {
+      int spos[NC / 2];  // class-sorted staging slot of my label cells
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) spos[k] = tab[3 * (NC / 2) * 32 + k * 32 + lane];
+      Inflow in;
+      inflow_prime<NC, 0>(s, in);
+      for_frames<NC, 0>(pblk, n, la, blank_off, [&](int r, const FProbs<NC>& pc) {
+        const float2* src = reinterpret_cast<const float2*>(rows + r * RS) + lane;
+        float2 w[NC / 2];
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) w[k] = src[k * 32];
+        fstep<NC, 0, false>(s, in, la, pc, nullptr);
+        __syncwarp();  // every lane has read row r before it becomes the staging area
+        float* gf = rows + r * RS;
+        float gb = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) {
+          gb = fmaf(s.x[2 * k], w[k].x, gb);
+          if (spos[k] >= 0) gf[spos[k]] = s.x[2 * k + 1] * w[k].y;
+        }
+        gf[F_SPAD + lane] = gb;
+        if (lane == 0) gf[F_SPAD + 32] = 0.f;  // the always-zero slot out-of-range class reads are pointed at
+      });
+    }
+    __syncwarp();
+    fstamp(P, uiter, nmine, 4);
+    // ---- per frame: class sums of the staged posteriors, gradient rows; FR frames interleaved.
+    // Staging is sorted by class, so a class is one contiguous range [cls[v], cls[v+1]): each lane adds up
+    // the ranges of its classes directly (independent loads, no scan).  The two warp-wide sums per frame (blank
+    // partials, total mass) go through the integer reduction unit in 2^-26 fixed point: one REDUX each
+    // instead of five dependent shuffle rounds.
+    constexpr int FR = 4;
+#pragma unroll 1
+    for (int r = 0; r < n; r += FR) {
+      const int nf = n - r < FR ? n - r : FR;
+      const float* gfp[FR];
+      float gbl[FR], gb[FR];
+#pragma unroll
+      for (int f = 0; f < FR; ++f) {
+        gfp[f] = rows + (f < nf ? r + f : r) * RS;
+        gbl[f] = gfp[f][F_SPAD + lane];
+      }
+#pragma unroll
+      for (int f = 0; f < FR; ++f) gb[f] = warp_sum_fx(gbl[f]);
+      float tot[FR];
+#pragma unroll
+      for (int f = 0; f < FR; ++f) tot[f] = gbl[f];
+#pragma unroll 1
+      for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
+        const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
+        const int ml = (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
+        float acc[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < ml; ++k) {
+          const int idx = ca + k < cb ? ca + k : F_SPAD + 32;  // out of range: a slot that always holds zero
+#pragma unroll
+          for (int f = 0; f < FR; ++f) acc[f] += gfp[f][idx];
+        }
+        float pv[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) pv[f] = v < V ? pblk[v * F_KS + (f < nf ? r + f : r)] : 0.f;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+          tot[f] += acc[f];
+          const float gv = acc[f] + (v == P.blank ? gb[f] : 0.f);
+          if (f < nf && v < V) st_stream(g_base + (int64_t)(t0 + r + f) * P.st + v, (pv[f] - gv) * scale);
+        }
+      }
+      // D3: the posteriors of a frame sum to one unless mass was lost to fp32 range somewhere
+#pragma unroll
+      for (int f = 0; f < FR; ++f) {
+        const float t = warp_sum_fx(tot[f]);
+        if (f < nf && !(fabsf(t - 1.f) <= F_MASS_TOL)) mass_ok = false;
+      }
+    }
+    __syncwarp();
+    i = i_next;
+  }
+  if (!mass_ok && lane == 0) atomicOr(&sc->uflag, 8);  // D3 (the sums are warp-uniform)
+}
+
+// ------------------------------------------------------------------ kernel
+template <int NC>
+__global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParams P) {
+  SSD_DYN_SMEM(smem);
+  const FastSmem M = fast_smem_layout(P.V, P.RS, P.S_max + 4, P.nb_max);
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  int* lab = reinterpret_cast<int*>(smem + M.lab_off);
+  int* pos = reinterpret_cast<int*>(smem + M.pos_off);
+  int* cls = reinterpret_cast<int*>(smem + M.cls_off);
+  int* tab = reinterpret_cast<int*>(smem + M.tab_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M.bar_off);
+  uint64_t* blk_ready = reinterpret_cast<uint64_t*>(smem + M.blk_off);
+  FastScal* sc = reinterpret_cast<FastScal*>(smem + M.scal_off);
+  uint64_t* z_ready = bars + FB_Z;
+
+  if (tid == 0) {
+    for (int i = 0; i < FB_TOTAL; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  // the dummy class (row V) of every probability block stays zero for the whole launch
+  for (int i = tid; i < (2 * F_NP + F_W) * F_K; i += F_THREADS) {
+    const int blk = i / F_K, r = i - blk * F_K;
+    unsigned char* base = blk < 2 * F_NP ? smem + M.main_off + (size_t)(blk / F_NP) * M.main_bytes + (size_t)(blk % F_NP) * M.p_slot
+                                         : smem + M.worker_off + (size_t)(blk - 2 * F_NP) * M.worker_bytes + M.wrow_bytes;
+    reinterpret_cast<float*>(base)[P.V * F_KS + r] = 0.f;
+  }
+  __syncthreads();
+
+  unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
+  unsigned qbase = 0u, uiter = 0u, nraw = 0u;
+  // Warp w issues from sub-partition w % 4.  Two CTAs share an SM: the second one to arrive swaps its
+  // mains and loaders (warps 0,1 <-> 2,3), so that each sub-partition carries ONE main sweep, one loader
+  // and two workers instead of two mains on two of them.
+  if (tid == 0) {
+#ifdef SSD_EMU
+    sc->rot = (int)(blockIdx.x & 1u);
+#else
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sc->rot = (int)(atomicAdd(P.sm_slot + smid, 1u) & 1u);
+#endif
+  }
+  __syncthreads();
+  const int rwarp = warp < 4 ? (warp ^ (sc->rot << 1)) : warp;  // role index: 0 MF, 1 MB, 2 LF, 3 LB, 4.. workers
+
+  for (;;) {
+    if (tid == 0) {
+      const int u = (int)atomicAdd(P.counter, 1u);
+      sc->utt = u;
+      if (u < P.B) {
+        const int b = P.order ? P.order[u] : u;
+        const int64_t tl = P.in_len[b], sl = P.tg_len[b];
+        const bool bad = tl < 0 || tl > P.T || sl < 0 || sl > P.S_max;
+        sc->b = b;
+        sc->T = bad ? 0 : (int)tl;
+        sc->S = bad ? 0 : (int)sl;
+        // everything that is not a plain utterance goes to the exact path unseen
+        sc->skip = (bad || tl == 0 || 2 * sl + 1 > 32 * NC) ? 1 : 0;
+        sc->uflag = sc->skip;
+        sc->next_blk = 0;
+        float mul = P.grad_mul ? *P.grad_mul : 1.f;
+        if (P.mean_den > 0) mul /= (float)((double)P.mean_den * (double)(sl > 1 ? sl : 1));
+        sc->scale = mul;
+      }
+    }
+    __syncthreads();
+    if (sc->utt >= P.B) break;
+    const int b = sc->b, S = sc->S;
+    for (int j = tid; j < S; j += F_THREADS) {
+      const int64_t y = P.targets[(int64_t)b * P.tgt_stride + j];
+      if (y < 0 || y >= P.V) sc->skip = sc->uflag = 1;  // benign race: every writer stores 1
+      lab[j] = (int)(y < 0 ? 0 : (y >= P.V ? P.V - 1 : y));
+    }
+    __syncthreads();
+    const bool skip = sc->skip != 0;
+    FPlan pl;
+    pl.b = b; pl.Tb = sc->T; pl.S = S; pl.L = 2 * S + 1;
+    pl.NB = (pl.Tb + F_K - 1) / F_K;
+    if (!skip) {
+      // class histogram -> start offsets; position of every label in class-sorted order (stable)
+      for (int v = tid; v < P.V; v += F_THREADS) {
+        int c = 0;
+        for (int j = 0; j < S; ++j) c += (lab[j] == v) ? 1 : 0;
+        cls[v + 1] = c;
+      }
+      for (int q = tid; q < pl.NB; q += F_THREADS) mbar_init(&blk_ready[q], 2);  // MF's and MB's checkpoint
+      __syncthreads();
+      if (tid == 0) {
+        cls[0] = 0;
+        for (int v = 0; v < P.V; ++v) cls[v + 1] += cls[v];
+      }
+      __syncthreads();
+      for (int j = tid; j < S; j += F_THREADS) {
+        const int y = lab[j];
+        int k = 0;
+        for (int i = 0; i < j; ++i) k += (lab[i] == y) ? 1 : 0;
+        pos[j] = cls[y] + k;
+      }
+      __syncthreads();
+      build_lane_tables<NC>(S, P.V, lab, pos, tab);
+      __syncthreads();
+      // rows the sweeps never visit: frames beyond the input length
+      if (P.grad) {
+        float* g0 = P.grad + (int64_t)b * P.sb;
+        for (int64_t r = pl.Tb + warp; r < P.T; r += F_THREADS / 32)
+          for (int v = lane; v < P.V; v += 32) st_stream(g0 + r * P.st + v, 0.f);
+      }
+      if (warp < 4) {
+        const int h = rwarp & 1;
+        MainView mv;
+        mv.base = smem + M.main_off + (size_t)h * M.main_bytes;
+        mv.bar = bars + h * FB_PER_MAIN;
+        mv.p_slot = M.p_slot;
+        mv.raw_slot = M.raw_slot;
+        if (rwarp == 0) fast_main<NC, 0>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
+        else if (rwarp == 1) fast_main<NC, 1>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
+        else if (rwarp == 2) fast_loader<0>(P, mv, pl, qbase, sc, uiter);
+        else fast_loader<1>(P, mv, pl, qbase, sc, uiter);
+      } else {
+        const int w = warp - 4;
+        unsigned char* wb = smem + M.worker_off + (size_t)w * M.worker_bytes;
+        WorkerView wv;
+        wv.rows = reinterpret_cast<float*>(wb);
+        wv.pblk = reinterpret_cast<float*>(wb + M.wrow_bytes);
+        wv.raw0 = reinterpret_cast<float*>(wb + M.wrow_bytes + M.p_slot);
+        wv.raw_stride = (int)(M.raw_slot / 4);
+        wv.rawbar = bars + FB_WRAW + 2 * w;
+        fast_worker<NC>(P, pl, tab, cls, wv, ckpt_cta, blk_ready, z_ready, uiter, nraw, sc);
+      }
+      qbase += (unsigned)pl.NB;
+      ++uiter;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int f = sc->uflag;
+      P.flags[b] = f;
+      if (f) atomicAdd(P.counter + 1, 1u);
+    }
+    __syncthreads();  // label tables and scalars are rebuilt for the next utterance
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct FastPlan {
+  int NC, RS, grid, nb_max;
+  size_t smem, ckpt_cta_bytes, ckpt_rec_bytes, ws_bytes;
+};
+
+static int fast_env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s && *s ? std::atoi(s) : dflt;
+}
+
+static int fast_device_sms() {
+#ifdef SSD_EMU
+  return 2;
+#else
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+#endif
+}
+
+static bool fast_plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, FastPlan& pl) {
+  if (fast_env_int("SSD_LOSS_EXACT", 0)) return false;  // force the fp64 path (tests, comparisons)
+  if (S_max > 255 || V > 128 || T < 1 || B < 1) return false;
+  const int need = (int)((2 * S_max + 1 + 31) / 32);
+  const int buckets[4] = {4, 8, 12, 16};
+  pl.NC = 0;
+  for (int i = 0; i < 4 && !pl.NC; ++i)
+    if (need <= buckets[i]) pl.NC = buckets[i];
+  if (need <= 14 && need > 12) pl.NC = 14;
+  if (!pl.NC) return false;
+  const int cells = 32 * pl.NC, stage = F_SPAD + 32 + 4;
+  pl.RS = ((cells > stage ? cells : stage) + 3) & ~3;
+  pl.nb_max = (int)((T + F_K - 1) / F_K);
+  pl.smem = fast_smem_layout((int)V, pl.RS, (int)S_max + 4, pl.nb_max).total;
+  if (pl.smem > 113 * 1024) return false;
+  const int64_t slots = (int64_t)fast_device_sms() * 2;
+  pl.grid = (int)(B < slots ? B : slots);
+  pl.ckpt_rec_bytes = (size_t)pl.NC * 32 * 4 + 128;
+  pl.ckpt_cta_bytes = (size_t)2 * pl.nb_max * pl.ckpt_rec_bytes;
+  pl.ws_bytes = 256 + 4096 + (((size_t)B * 4 + 255) & ~(size_t)255) + (size_t)pl.grid * pl.ckpt_cta_bytes + (size_t)8 * F_TLOG_N * F_TLOG_S * 8;
+  return true;
+}
+
+size_t loss_fast_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
+  FastPlan pl;
+  return fast_plan_for(B, T, V, S_max, pl) ? pl.ws_bytes : 0;
+}
+
+template <int NC>
+static int loss_fast_launch_t(FastParams& P, const FastPlan& pl, cudaStream_t stream) {
+  auto kfn = loss_fast_kernel<NC>;
+#ifndef SSD_EMU
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss(fast): cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
+  e = cudaMemsetAsync(P.counter, 0, 256, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(P.sm_slot, 0, 4096, stream);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss(fast): cudaMemsetAsync: %s", cudaGetErrorString(e));
+#else
+  P.counter[0] = P.counter[1] = 0u;
+#endif
+  SSD_LAUNCH(kfn, (unsigned)pl.grid, F_THREADS, pl.smem, stream, P);
+  return check_launch("loss_fast_kernel");
+}
+
+// Returns SSD_OK and sets *flags / *nflag (device pointers into ws) when the fast path ran,
+// SSD_ERR_UNSUPPORTED (without touching the error text) when it does not apply.
+int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
+                     int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
+                     int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
+                     size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream) {
+  FastPlan pl;
+  if (!fast_plan_for(B, T, V, S_max, pl)) return SSD_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
+  FastParams P;
+  P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
+  P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
+  P.in_len = in_len; P.tg_len = tg_len; P.order = order;
+  P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;
+  P.nll = nll; P.grad = grad;
+  unsigned char* w = reinterpret_cast<unsigned char*>(ws);
+  P.counter = reinterpret_cast<unsigned*>(w);
+  P.flags = reinterpret_cast<int*>(w + 256);
+  P.sm_slot = reinterpret_cast<unsigned*>(w + 256 + (((size_t)B * 4 + 255) & ~(size_t)255));
+  P.ckpt = w + 256 + (((size_t)B * 4 + 255) & ~(size_t)255) + 4096;
+  P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nb_max = pl.nb_max;
+  P.RS = pl.RS;
+  P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
+  if (fast_env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;
+  P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)8 * F_TLOG_N * F_TLOG_S * 8) : nullptr;
+  *flags = P.flags;
+  *nflag = P.counter + 1;
+  switch (pl.NC) {
+    case 4: return loss_fast_launch_t<4>(P, pl, stream);
+    case 8: return loss_fast_launch_t<8>(P, pl, stream);
+    case 12: return loss_fast_launch_t<12>(P, pl, stream);
+    case 14: return loss_fast_launch_t<14>(P, pl, stream);
+    default: return loss_fast_launch_t<16>(P, pl, stream);
+  }
+}
+
+}  // namespace ssd

@@ -37,6 +37,7 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
                 int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+size_t loss_fallback_counter_offset(int64_t B, int64_t T, int64_t V, int64_t S_max);
 int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
                 int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
                 int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,

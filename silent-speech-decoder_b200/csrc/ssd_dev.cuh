@@ -101,6 +101,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// For waits that are expected to be long (a producer far ahead of its consumer, a worker waiting for
+// its first block): back off between polls so that the issue slots go to the warps with work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#ifdef SSD_EMU
+  emu::mbar_wait(bar, parity);
+#else
+  while (!mbar_test(bar, parity)) __nanosleep(200);
+#endif
+}
+
 // ------------------------------------------------------------------ TMA 1-D bulk copy
 // global -> shared::cta, completion counted in bytes on `bar`.  dst, src and bytes must be
 // multiples of 16.  One thread issues; the copy engine moves the data.

@@ -175,5 +175,24 @@ def ctc_loss_fwd_bwd(
                                        gm.data_ptr() if gm is not None else None, nll.data_ptr(),
                                        grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
                                        _stream_ptr(dev)))
-            LAUNCHES["loss"] += 1
+            # fp32 fast-path kernel + the fp64 kernel over whatever it flagged, or the fp64 kernel alone
+            two = int(lib.ssd_ctc_loss_fallback_counter_offset(B, T, V, S)) != _NO_FAST
+            LAUNCHES["loss"] += 2 if two else 1
     return nll, grad
+
+
+_NO_FAST = 2 ** 64 - 1
+
+
+def loss_fallback_count(B: int, T: int, V: int, S: int, device=None) -> Optional[int]:
+    """How many utterances of the LAST ctc_loss_fwd_bwd call of this shape were recomputed by the exact fp64
+    kernel (flagged by the fp32 fast path); None if the fast path does not cover the shape. Synchronises."""
+    lib = _native.load()
+    off = int(lib.ssd_ctc_loss_fallback_counter_offset(B, T, V, S))
+    if off == _NO_FAST:
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = _WS.get((dev.index if dev.index is not None else torch.cuda.current_device(), "loss"))
+    if ws is None or ws.numel() < off + 4:
+        return None
+    return int(ws[off:off + 4].view(torch.int32).item())

@@ -19,7 +19,7 @@ REPO = HERE.parent.parent
 CSRC = REPO / "silent-speech-decoder_b200" / "csrc"
 OUT = HERE / "_build"
 LIB = OUT / "libssd_ctc_emu.so"
-SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "capi.cu"]
+SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "capi.cu"]
 
 
 def build(force: bool = False) -> Path:
@@ -82,7 +82,7 @@ def beam(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, width: 
 
 
 def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity: bool = True, mean_den: int = 0,
-         want_grad: bool = True, grad_mul=None):
+         want_grad: bool = True, grad_mul=None, with_fallbacks: bool = False):
     lp = np.ascontiguousarray(lp, dtype=np.float32)
     B, T, V = lp.shape
     il = np.asarray(in_len, dtype=np.int64)
@@ -96,4 +96,10 @@ def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity
     gm = None if grad_mul is None else np.asarray([grad_mul], dtype=np.float32)
     lib.check(lib.ssd_ctc_loss(_ptr(lp), B, T, V, T * V, V, _ptr(tg), S, S, _ptr(il), _ptr(tl), None, blank, int(zero_infinity),
                                mean_den, _ptr(gm), _ptr(nll), _ptr(grad), _ptr(ws), ws.nbytes, None))
+    if with_fallbacks:  # utterances that took the exact fp64 path (None: the fast path does not cover the shape)
+        off = lib.ssd_ctc_loss_fallback_counter_offset(B, T, V, S)
+        nfb = None if off == 2 ** 64 - 1 else int(ws.view(np.uint32)[off // 4])
+        if with_fallbacks == "flags":  # per-utterance reason bits (FastParams::flags follows the counters)
+            return nll, grad, None if nfb is None else ws.view(np.int32)[(off - 4 + 256) // 4:(off - 4 + 256) // 4 + B].copy()
+        return nll, grad, nfb
     return nll, grad

@@ -463,6 +463,7 @@ inline unsigned __float_as_uint(float f) { return (unsigned)emu_to_bits(f); }
 inline float __uint_as_float(unsigned v) { return emu_from_bits<float>((uint64_t)v); }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+inline int __float2int_rn(float f) { return (int)std::lrintf(f); }
 inline float __expf(float x) { return std::exp(x); }
 inline float __logf(float x) { return std::log(x); }
 
