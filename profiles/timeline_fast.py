@@ -1,4 +1,5 @@
-"""Per-role block timeline of CTA 0's first utterance in the fp32 fast loss kernel (SSD_LOSS_DBG=8)."""
+"""Per-role block timeline of CTA 0's first utterance in the fp32 fast loss kernel (SSD_LOSS_DBG=8).
+Needs the stamped build: SSD_NVCC_FLAGS=-DSSD_LOSS_TIMELINE python -m silent_speech_decoder_b200.build --force"""
 import os, sys
 os.environ["SSD_LOSS_DBG"] = "8"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,11 +13,12 @@ for _ in range(2):
 torch.cuda.synchronize()
 ws = ops._WS[(0, "loss")]
 N, S = 256, 6
-log = ws[-8 * N * S * 8:].view(torch.int64).cpu().numpy().reshape(8, N, S)
+NW = 10
+log = ws[-NW * N * S * 8:].view(torch.int64).cpu().numpy().reshape(NW, N, S)
 t0 = log[:, :, :5][log[:, :, :5] > 0].min()
 print("utterance 0: S =", int(tl[0]), " cycles since first stamp")
-names = ["MF", "MB", "LF", "LB", "W0", "W1", "W2", "W3"]
-for w in range(8):
+names = ["w0 MF", "w1 MB", "w2 W0", "w3 W1", "w4 W2", "w5 W3", "w6 W4", "w7 W5", "w8 LF", "w9 LB"]  # role map of an unrotated CTA
+for w in range(NW):
     a = log[w]
     idx = np.where(a[:, 0] > 0)[0]
     if len(idx) == 0:
@@ -26,4 +28,4 @@ for w in range(8):
     for i in sel:
         st = [int(v - t0) if v > 0 else -1 for v in a[i, :5]]
         d = [st[k + 1] - st[k] if st[k + 1] >= 0 and st[k] >= 0 else None for k in range(4)]
-        print(f"   ev {i:3d} q={a[i, 5] if w >= 4 else '-'} stamps {st}  deltas {d}")
+        print(f"   ev {i:3d} q={a[i, 5] if 2 <= w <= 7 else '-'} stamps {st}  deltas {d}")

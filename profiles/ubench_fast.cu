@@ -14,11 +14,11 @@ __global__ void bench(const float* pglob, int nblocks, long long* out, float* si
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int V = 48;
-  for (int i = threadIdx.x; i < (V + 1) * F_K; i += blockDim.x) sm[i] = i < V * F_K ? pglob[i] : 0.f;
+  for (int i = threadIdx.x; i < (V + 1) * F_KS; i += blockDim.x) sm[i] = i < V * F_KS ? pglob[i % 392] : 0.f;
   __syncthreads();
   FLabels<NC> lt;
   for (int k = 0; k < NC / 2; ++k) {
-    lt.off[k] = ((lane * 7 + k * 3) % V) * F_K * 4;
+    lt.off[k] = ((lane * 7 + k * 3) % V) * F_KS * 4;
     lt.skf[k] = (k + lane) & 1 ? 1.f : 0.f;
   }
   FStrip<NC> s;
@@ -27,10 +27,10 @@ __global__ void bench(const float* pglob, int nblocks, long long* out, float* si
   for (int i = 0; i < NC; ++i) s.x[i] = 1.f + 0.01f * i;
   Inflow in;
   inflow_prime<NC, DIR>(s, in);
-  const int blank_off = 1 * F_K * 4;
+  const int blank_off = 1 * F_KS * 4;
   long long t0 = clock64();
   for (int b = 0; b < nblocks; ++b) {
-    for_frames<NC, DIR>(sm, F_K, lt, blank_off, [&](int, const FProbs<NC>& pc) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr); });
+    for_frames<NC, DIR>(sm, 0, F_K, lt, blank_off, [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr, mid); });
     if (MODE >= 1) {
       renorm_exchange<NC, DIR>(s);
       inflow_prime<NC, DIR>(s, in);
@@ -55,8 +55,8 @@ void run(const char* name, int warps) {
   cudaMalloc(&out, 1024 * 8);
   cudaMalloc(&sink, 1024 * 32 * 4);
   const int nb = 200;
-  bench<NC, DIR, MODE><<<1, 32 * warps, 49 * 8 * 4>>>(p, nb, out, sink);
-  bench<NC, DIR, MODE><<<1, 32 * warps, 49 * 8 * 4>>>(p, nb, out, sink);
+  bench<NC, DIR, MODE><<<1, 32 * warps, 49 * 9 * 4>>>(p, nb, out, sink);
+  bench<NC, DIR, MODE><<<1, 32 * warps, 49 * 9 * 4>>>(p, nb, out, sink);
   cudaDeviceSynchronize();
   long long ho[64];
   cudaMemcpy(ho, out, warps * 8, cudaMemcpyDeviceToHost);

@@ -56,7 +56,8 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: str) -> Path:
         obj = OBJ_DIR / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
+        extra = os.environ.get("SSD_NVCC_FLAGS", "").split()  # e.g. -DSSD_LOSS_TIMELINE for profiles/timeline_fast.py
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:

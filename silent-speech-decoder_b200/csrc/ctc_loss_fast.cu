@@ -40,10 +40,26 @@ namespace ssd {
 constexpr int F_K = 8;          // frames per block = renormalisation and checkpoint interval
 constexpr int F_KS = 9;         // class-row stride of a probability block in floats: odd, so that a warp's gather of 32
                                 // different classes at one frame touches 32 different banks (stride 8 folds them onto 4)
-constexpr int F_THREADS = 256;  // MF MB LF LB + 4 workers
-constexpr int F_W = 4;
+// Worker shape.  Default: 4 workers, whole blocks (8 warps, 128 registers).  -DSSD_F_W=6 -DSSD_F_H=4 selects the
+// other point tried: 6 workers whose row buffers hold half a block (the block is done as two passes of 4 frames,
+// the upper half's beta swept once more without stores); its 10 warps cap registers at 96 and the spills made
+// it slower (562 us vs 393 us at config 2), see DESIGN.md.
+#ifndef SSD_F_W
+#define SSD_F_W 4
+#endif
+#ifndef SSD_F_H
+#define SSD_F_H 8
+#endif
+constexpr int F_W = SSD_F_W;      // block workers
+constexpr int F_THREADS = 32 * (4 + F_W);  // MF MB LF LB + workers
+constexpr int F_H = SSD_F_H;      // frames per worker pass (rows a worker buffers)
+static_assert((F_W == 4 || F_W == 6) && (F_H == 4 || F_H == 8), "supported worker shapes");
 constexpr int F_NP = 3;    // probability-row ring depth per main (blocks)
 constexpr int F_NRAW = 3;  // raw-row ring depth per main
+#ifndef SSD_F_FR
+#define SSD_F_FR 4
+#endif
+constexpr int F_FR = SSD_F_FR;  // frames interleaved in the gradient stage
 constexpr int F_TOP = 40;  // renormalised strips have their largest cell in [2^40, 2^41)
 constexpr int F_SPAD = 256;  // label staging capacity (S <= 255 on this path)
 constexpr float F_MASS_TOL = 1.5e-5f;
@@ -65,19 +81,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 #endif
 }
-// exp(lp), branch free and with ONE slow-pipe instruction (MUFU.EX2): round-to-nearest by the magic-number
-// add, the argument split so that its rounding does not scale with |lp|, the integer part added straight
-// into the exponent field.  Inputs outside +-F_LP_ABS (flagged by the caller, D1) give a harmless finite value.
-__device__ __forceinline__ float prob_f(float lp) {
-  const float MAGIC = 12582912.f;  // 1.5 * 2^23: t + MAGIC holds rint(t) in its low mantissa bits
-  const float t = fminf(fmaxf(lp * 1.4426950408889634f, -125.f), 125.f);
-  const float kf = t + MAGIC;
-  const float kr = kf - MAGIC;
-  float r = fmaf(lp, 1.4426950216293335f, -kr);  // log2(e) high part
-  r = fmaf(lp, 1.9259629911266175e-8f, r);       // log2(e) low part
-  r = fminf(fmaxf(r, -1.f), 1.f);                // only binds outside the flagged range
-  return __int_as_float(__float_as_int(ex2_approx(r)) + (__float_as_int(kf) << 23));
-}
+// exp(lp) = ex2(lp * log2 e): two instructions.  The rounding of the product costs |lp * log2 e| * 2^-24 relative
+// (3e-7 at lp = -4, 2e-6 at lp = -20), i.e. it acts like a perturbation of the input far below the 1e-5 the
+// result is held to; inputs beyond +-F_LP_ABS are flagged by the caller (D1) and never reach a result.
+__device__ __forceinline__ float prob_f(float lp) { return ex2_approx(lp * 1.4426950408889634f); }
 __device__ __forceinline__ float ld_cg(const float* p) {
 #ifdef SSD_EMU
   return *p;
@@ -125,12 +132,13 @@ struct FastParams {
   int nb_max;
   int RS;  // worker row stride in floats
   int use_tma;
-  long long* tlog;  // SSD_LOSS_DBG & 8: [8 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
+  long long* tlog;  // SSD_LOSS_DBG & 8: [F_THREADS/32 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
 };
 constexpr int F_TLOG_N = 256, F_TLOG_S = 6;
 
+// compiled in only with -DSSD_LOSS_TIMELINE (profiles/timeline_fast.py builds that variant)
 __device__ __forceinline__ void fstamp(const FastParams& P, unsigned uiter, int idx, int slot, long long tag = -1) {
-#ifndef SSD_EMU
+#if !defined(SSD_EMU) && defined(SSD_LOSS_TIMELINE)
   if (P.tlog && blockIdx.x == 0 && uiter == 0 && idx < F_TLOG_N && (threadIdx.x & 31) == 0)
     P.tlog[(((int)threadIdx.x >> 5) * F_TLOG_N + idx) * F_TLOG_S + slot] = tag >= 0 ? tag : clock64();
 #endif
@@ -154,7 +162,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(int V, int RS, int S_tab, i
   m.p_slot = al((size_t)(V + 1) * F_KS * 4 + 16);
   m.raw_slot = al((size_t)F_K * V * 4);
   m.main_bytes = F_NP * m.p_slot + F_NRAW * m.raw_slot;
-  m.wrow_bytes = al((size_t)F_K * RS * 4);
+  m.wrow_bytes = al((size_t)F_H * RS * 4);
   m.worker_bytes = m.wrow_bytes + m.p_slot + 2 * m.raw_slot;
   size_t o = 0;
   m.main_off = o; o += 2 * m.main_bytes;
@@ -248,6 +256,7 @@ typedef const char* saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const void* p) { return reinterpret_cast<const char*>(p); }
 template <int IMM>
 __device__ __forceinline__ float lds_pinned(saddr_t a) { return *reinterpret_cast<const float*>(a + IMM); }
+__device__ __forceinline__ saddr_t sadd(saddr_t a, int d) { return a + d; }
 #else
 typedef uint32_t saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const void* p) { return smem_u32(p); }
@@ -259,6 +268,7 @@ __device__ __forceinline__ float lds_pinned(saddr_t a) {
   asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(IMM));
   return v;
 }
+__device__ __forceinline__ saddr_t sadd(saddr_t a, int d) { return a + (uint32_t)d; }
 #endif
 template <int NC>
 struct PPtr {
@@ -272,29 +282,33 @@ __device__ __forceinline__ void load_probs(FProbs<NC>& p, const PPtr<NC>& pp) {
   for (int k = 0; k < NC / 2; ++k) p.lab[k] = lds_pinned<IMM>(pp.lab[k]);
 }
 template <int NC, int DIR, class F>
-__device__ __forceinline__ void for_frames(const float* pblk, int n, const FLabels<NC>& lt, int blank_off, F&& body) {
+__device__ __forceinline__ void for_frames(const float* pblk, int f0, int n, const FLabels<NC>& lt, int blank_off, F&& body) {
   constexpr int D = DIR ? -4 : 4;
-  const saddr_t base = saddr_of(pblk) + (DIR ? (n - 1) * 4 : 0);
+  const saddr_t base = sadd(saddr_of(pblk), (DIR ? f0 + n - 1 : f0) * 4);
   PPtr<NC> pp;
-  pp.blank = base + blank_off;
+  pp.blank = sadd(base, blank_off);
 #pragma unroll
-  for (int k = 0; k < NC / 2; ++k) pp.lab[k] = base + lt.off[k];
+  for (int k = 0; k < NC / 2; ++k) pp.lab[k] = sadd(base, lt.off[k]);
   FProbs<NC> A, B;
   load_probs<NC, 0>(A, pp);
 #pragma unroll 1
   for (int rr = 0; rr < n; rr += 2) {
-    const int r = DIR ? n - 1 - rr : rr;
+    const int r = DIR ? f0 + n - 1 - rr : f0 + rr;
     const bool two = rr + 1 < n;
-    if (two) load_probs<NC, D>(B, pp);
-    body(r, A);
+    const bool more = rr + 2 < n;
+    // each step gets the other register set's loads as its mid-step hook
+    body(r, A, [&]() {
+      if (two) load_probs<NC, D>(B, pp);
+    });
     if (two) {
-      if (rr + 2 < n) {
-        pp.blank += 2 * D;
+      body(DIR ? r - 1 : r + 1, B, [&]() {
+        if (more) {
+          pp.blank = sadd(pp.blank, 2 * D);
 #pragma unroll
-        for (int k = 0; k < NC / 2; ++k) pp.lab[k] += 2 * D;
-        load_probs<NC, 0>(A, pp);
-      }
-      body(DIR ? r - 1 : r + 1, B);
+          for (int k = 0; k < NC / 2; ++k) pp.lab[k] = sadd(pp.lab[k], 2 * D);
+          load_probs<NC, 0>(A, pp);
+        }
+      });
     }
   }
 }
@@ -320,8 +334,13 @@ __device__ __forceinline__ void inflow_prime(const FStrip<NC>& s, Inflow& in) {
     in.b = __shfl_down_sync(FULL, s.x[1], 1);
   }
 }
-template <int NC, int DIR, bool SUMS>
-__device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<NC>& lt, const FProbs<NC>& p, float* sums) {
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `mid` runs right after the shuffles are issued: the place for the next frame's shared-memory loads, which
+// would otherwise sit in the memory pipe in front of the shuffles and delay them
+template <int NC, int DIR, bool SUMS, class H = NoHook>
+__device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<NC>& lt, const FProbs<NC>& p, float* sums, H&& mid = NoHook()) {
   float (&x)[NC] = s.x;
   Inflow nxt;
   auto cell = [&](int i, float a1, float a2) {
@@ -340,6 +359,7 @@ __device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<N
     cell(NC - 1, x[NC - 2], x[NC - 3]);
     nxt.a = __shfl_up_sync(FULL, x[NC - 1], 1);
     nxt.b = 0.f;
+    mid();
 #pragma unroll
     for (int i = NC - 2; i >= 2; --i) cell(i, x[i - 1], x[i - 2]);
     const float n1 = in.a * s.fin;  // lane 0: fin = 0
@@ -351,6 +371,7 @@ __device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<N
     cell(1, x[2], x[3]);
     nxt.a = __shfl_down_sync(FULL, x[0], 1);
     nxt.b = __shfl_down_sync(FULL, x[1], 1);
+    mid();
 #pragma unroll
     for (int i = 2; i < NC - 1; ++i) cell(i, x[i + 1], x[i + 2 < NC ? i + 2 : NC - 1]);
     const float m0 = in.a * s.fin, m1 = in.b * s.fin;  // lane 31: fin = 0
@@ -467,7 +488,7 @@ template <bool SMEM>
 __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
                                                float* __restrict__ pblk) {
   const int lane = lane_id();
-  int bad = 0;
+  float amax = 0.f;  // largest |log-prob| seen (a NaN passes here and poisons Z or a frame's mass instead)
   for (int base = 0; base < 2 * V; base += 64) {
     float lp[2][4];
     int vv[2], hh[2];
@@ -489,7 +510,7 @@ __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, co
       float pr[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        bad |= !(fabsf(lp[u][j]) <= F_LP_ABS);
+        amax = fmaxf(amax, fabsf(lp[u][j]));
         const float pv = prob_f(lp[u][j]);
         pr[j] = hh[u] * 4 + j < n ? pv : 0.f;
       }
@@ -500,7 +521,7 @@ __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, co
       }
     }
   }
-  return bad;
+  return amax > F_LP_ABS ? 1 : 0;
 }
 // one loop per source: the unused path's address arithmetic would otherwise ride along predicated off
 __device__ __forceinline__ int convert_block(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
@@ -589,7 +610,7 @@ __device__ void fast_main(const FastParams& P, const MainView& mv, const FPlan& 
     fstamp(P, uiter, bi, 1);
     const float* pblk = mv.p(slot);
     const int n = min(F_K, pl.Tb - q * F_K);
-    for_frames<NC, DIR>(pblk, n, lt, blank_off, [&](int, const FProbs<NC>& pc) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr); });
+    for_frames<NC, DIR>(pblk, 0, n, lt, blank_off, [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr, mid); });
     __syncwarp();
     if (lane == 0) mbar_arrive(&mv.bar[FB_PEMPTY + slot]);
     fstamp(P, uiter, bi, 2);
@@ -608,7 +629,7 @@ __device__ void fast_main(const FastParams& P, const MainView& mv, const FPlan& 
 
 // ------------------------------------------------------------------ W: block workers
 struct WorkerView {
-  float* rows;   // [F_K][RS]: beta~ rows, then (same storage) the staged posteriors
+  float* rows;   // [F_H][RS]: beta~ rows of the half in flight, then (same storage) the staged posteriors
   float* pblk;   // class-major probabilities of the block in flight
   float* raw0;   // two TMA landing buffers (one block ahead), raw_stride floats apart
   int raw_stride;
@@ -620,7 +641,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
                             const int* __restrict__ cls, const WorkerView& wv, const unsigned char* ckpt_cta, uint64_t* blk_ready,
                             uint64_t* z_ready, unsigned uiter, unsigned& nraw, FastScal* sc) {
   const int lane = lane_id();
-  const int V = P.V, RS = P.RS, S = pl.S;
+  const int V = P.V, RS = P.RS;
   const int blank_off = P.blank * F_KS * 4;  // bytes
   const bool want_grad = P.grad != nullptr;
   float* rows = wv.rows;
@@ -678,168 +699,184 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     fstamp(P, uiter, nmine, 2);
     fstamp(P, uiter, nmine, 5, q);
     __syncwarp();
-    // ---- beta backwards over the block: pre-emission sums -> rows
-    FStrip<NC> s;
-    ckpt_load<NC>(ck_b + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
-    const int e_beta = s.e;
-    s.fin = fin_of<1>(s.e);
-    {
-      FLabels<NC> lb;
-      load_labels<NC, 1>(lb, tab);
-      Inflow in;
-      inflow_prime<NC, 1>(s, in);
-      for_frames<NC, 1>(pblk, n, lb, blank_off, [&](int r, const FProbs<NC>& pc) {
-        float sums[NC];
-        fstep<NC, 1, true>(s, in, lb, pc, sums);
-        float2* dst = reinterpret_cast<float2*>(rows + r * RS) + lane;
+    // ---- the block in halves of F_H frames (lower half first: alpha runs upwards through both)
+    FStrip<NC> sa;  // alpha state, carried from the lower half into the upper
+    Inflow ina;
+    int e_alpha = 0, e_beta = 0;
+    bool stop = false;
+#pragma unroll 1
+    for (int f0 = 0; f0 < n; f0 += F_H) {
+      const int nh = min(F_H, n - f0);
+      // ---- beta backwards: pre-emission sums of this half's frames -> rows.  Its start state is the block's
+      // checkpoint swept (without stores) down through the frames above this half.
+      {
+        FStrip<NC> s;
+        ckpt_load<NC>(ck_b + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
+        e_beta = s.e;
+        s.fin = fin_of<1>(s.e);
+        FLabels<NC> lb;
+        load_labels<NC, 1>(lb, tab);
+        Inflow in;
+        inflow_prime<NC, 1>(s, in);
+        if (f0 + nh < n)
+          for_frames<NC, 1>(pblk, f0 + nh, n - f0 - nh, lb, blank_off,
+                            [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, 1, false>(s, in, lb, pc, nullptr, mid); });
+        for_frames<NC, 1>(pblk, f0, nh, lb, blank_off, [&](int r, const FProbs<NC>& pc, auto&& mid) {
+          float sums[NC];
+          fstep<NC, 1, true>(s, in, lb, pc, sums, mid);
+          float2* dst = reinterpret_cast<float2*>(rows + (r - f0) * RS) + lane;
 #pragma unroll
-        for (int k = 0; k < NC / 2; ++k) dst[k * 32] = make_float2(sums[2 * k], sums[2 * k + 1]);
-      });
-    }
-    __syncwarp();
-    fstamp(P, uiter, nmine, 3);
-    // ---- alpha forwards
-    ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
-    const int e_alpha = s.e;
-    FLabels<NC> la;
-    load_labels<NC, 0>(la, tab);
-    if (i == 0) {
-      // Z = sum over the lattice of alpha_t * beta~_t at the block's first frame (unscaled pass)
-      FStrip<NC> z = s;
-      z.fin = fin_of<0>(z.e);
-      Inflow zin;
-      inflow_prime<NC, 0>(z, zin);
-      FProbs<NC> pc;
-      pc.blank = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + blank_off);
-#pragma unroll
-      for (int k = 0; k < NC / 2; ++k) pc.lab[k] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + la.off[k]);
-      fstep<NC, 0, false>(z, zin, la, pc, nullptr);
-      const float2* src = reinterpret_cast<const float2*>(rows) + lane;
-      float sl = 0.f;
-#pragma unroll
-      for (int k = 0; k < NC / 2; ++k) {
-        const float2 w = src[k * 32];
-        sl = fmaf(z.x[2 * k], w.x, sl);
-        sl = fmaf(z.x[2 * k + 1], w.y, sl);
-      }
-      const bool okl = sl >= 1.17549435e-38f && sl < 3.0e38f;
-      const int q_l = e_alpha + e_beta;
-      const int key = okl ? q_l + expo_f(sl) : -(1 << 30);
-      const int Qm = __reduce_max_sync(FULL, key);
-      const bool bad_lane = !(sl >= 0.f && sl < 3.0e38f);  // NaN / inf somewhere
-      const bool any_bad = __any_sync(FULL, bad_lane);
-      float inv_zm = 0.f;
-      int ez = 0;
-      const bool feasible = Qm > -(1 << 30) && !any_bad;
-      if (feasible) {
-        // every lane's partial in units of 2^Qm: at most 2 each, negligible ones flush
-        float tot = okl ? sl * pow2c(q_l - Qm) : 0.f;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-        const int et = expo_f(tot);
-        const float zm = tot * pow2c(-et);  // [1,2)
-        inv_zm = 1.f / zm;
-        ez = Qm + et;
-        if (lane == 0) P.nll[pl.b] = (float)(-(log((double)zm) + (double)ez * 0.69314718055994530942));
-      } else if (lane == 0) {
-        atomicOr(&sc->uflag, 16);  // D4: infeasible or lost -- the exact path decides which
-      }
-      if (lane == 0) {
-        sc->inv_zm = inv_zm;
-        sc->ez = ez;
+          for (int k = 0; k < NC / 2; ++k) dst[k * 32] = make_float2(sums[2 * k], sums[2 * k + 1]);
+        });
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(z_ready);
-    }
-    if (!want_grad) break;
-    mbar_wait_relaxed(z_ready, uiter & 1u);
-    {
-      // run alpha pre-scaled by c = 2^(e_alpha + e_beta - eZ) / Zm: the products below are posteriors
-      const float c = pow2c(e_alpha + e_beta - sc->ez) * sc->inv_zm;
+      fstamp(P, uiter, nmine, 3);
+      // ---- alpha forwards
+      FLabels<NC> la;
+      load_labels<NC, 0>(la, tab);
+      if (f0 == 0) {
+        ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, sa, pl.L);
+        e_alpha = sa.e;
+        if (i == 0) {
+          // Z = sum over the lattice of alpha_t * beta~_t at the block's first frame (unscaled pass)
+          FStrip<NC> z = sa;
+          z.fin = fin_of<0>(z.e);
+          Inflow zin;
+          inflow_prime<NC, 0>(z, zin);
+          FProbs<NC> pc;
+          pc.blank = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + blank_off);
 #pragma unroll
-      for (int k = 0; k < NC; ++k) s.x[k] *= c;
-      // inflow = x_nb * 2^(ea_nb - ea_me) * c_me / c_nb = x_nb * 2^(eb_me - eb_nb)
-      const int eb_nb = __shfl_up_sync(FULL, e_beta, 1);
-      s.fin = lane == 0 ? 0.f : pow2c(e_beta - eb_nb);
-    }
-    {
-      int spos[NC / 2];  // class-sorted staging slot of my label cells
+          for (int k = 0; k < NC / 2; ++k) pc.lab[k] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + la.off[k]);
+          fstep<NC, 0, false>(z, zin, la, pc, nullptr);
+          const float2* src = reinterpret_cast<const float2*>(rows) + lane;
+          float sl = 0.f;
 #pragma unroll
-      for (int k = 0; k < NC / 2; ++k) spos[k] = tab[3 * (NC / 2) * 32 + k * 32 + lane];
-      Inflow in;
-      inflow_prime<NC, 0>(s, in);
-      for_frames<NC, 0>(pblk, n, la, blank_off, [&](int r, const FProbs<NC>& pc) {
-        const float2* src = reinterpret_cast<const float2*>(rows + r * RS) + lane;
-        float2 w[NC / 2];
+          for (int k = 0; k < NC / 2; ++k) {
+            const float2 w = src[k * 32];
+            sl = fmaf(z.x[2 * k], w.x, sl);
+            sl = fmaf(z.x[2 * k + 1], w.y, sl);
+          }
+          const bool okl = sl >= 1.17549435e-38f && sl < 3.0e38f;
+          const int q_l = e_alpha + e_beta;
+          const int key = okl ? q_l + expo_f(sl) : -(1 << 30);
+          const int Qm = __reduce_max_sync(FULL, key);
+          const bool bad_lane = !(sl >= 0.f && sl < 3.0e38f);  // NaN / inf somewhere
+          const bool any_bad = __any_sync(FULL, bad_lane);
+          float inv_zm = 0.f;
+          int ez = 0;
+          const bool feasible = Qm > -(1 << 30) && !any_bad;
+          if (feasible) {
+            // every lane's partial in units of 2^Qm: at most 2 each, negligible ones flush
+            float tot = okl ? sl * pow2c(q_l - Qm) : 0.f;
 #pragma unroll
-        for (int k = 0; k < NC / 2; ++k) w[k] = src[k * 32];
-        fstep<NC, 0, false>(s, in, la, pc, nullptr);
-        __syncwarp();  // every lane has read row r before it becomes the staging area
-        float* gf = rows + r * RS;
-        float gb = 0.f;
-#pragma unroll
-        for (int k = 0; k < NC / 2; ++k) {
-          gb = fmaf(s.x[2 * k], w[k].x, gb);
-          if (spos[k] >= 0) gf[spos[k]] = s.x[2 * k + 1] * w[k].y;
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            const int et = expo_f(tot);
+            const float zm = tot * pow2c(-et);  // [1,2)
+            inv_zm = 1.f / zm;
+            ez = Qm + et;
+            if (lane == 0) P.nll[pl.b] = (float)(-(log((double)zm) + (double)ez * 0.69314718055994530942));
+          } else if (lane == 0) {
+            atomicOr(&sc->uflag, 16);  // D4: infeasible or lost -- the exact path decides which
+          }
+          if (lane == 0) {
+            sc->inv_zm = inv_zm;
+            sc->ez = ez;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(z_ready);
         }
-        gf[F_SPAD + lane] = gb;
-        if (lane == 0) gf[F_SPAD + 32] = 0.f;  // the always-zero slot out-of-range class reads are pointed at
-      });
-    }
-    __syncwarp();
-    fstamp(P, uiter, nmine, 4);
-    // ---- per frame: class sums of the staged posteriors, gradient rows; FR frames interleaved.
-    // Staging is sorted by class, so a class is one contiguous range [cls[v], cls[v+1]): each lane adds up
-    // the ranges of its classes directly (independent loads, no scan).  The two warp-wide sums per frame (blank
-    // partials, total mass) go through the integer reduction unit in 2^-26 fixed point: one REDUX each
-    // instead of five dependent shuffle rounds.
-    constexpr int FR = 4;
-#pragma unroll 1
-    for (int r = 0; r < n; r += FR) {
-      const int nf = n - r < FR ? n - r : FR;
-      const float* gfp[FR];
-      float gbl[FR], gb[FR];
+        if (!want_grad) {
+          stop = true;
+          break;
+        }
+        mbar_wait_relaxed(z_ready, uiter & 1u);
+        // run alpha pre-scaled by c = 2^(e_alpha + e_beta - eZ) / Zm: the products below are posteriors
+        const float c = pow2c(e_alpha + e_beta - sc->ez) * sc->inv_zm;
 #pragma unroll
-      for (int f = 0; f < FR; ++f) {
-        gfp[f] = rows + (f < nf ? r + f : r) * RS;
-        gbl[f] = gfp[f][F_SPAD + lane];
+        for (int k = 0; k < NC; ++k) sa.x[k] *= c;
+        // inflow = x_nb * 2^(ea_nb - ea_me) * c_me / c_nb = x_nb * 2^(eb_me - eb_nb)
+        const int eb_nb = __shfl_up_sync(FULL, e_beta, 1);
+        sa.fin = lane == 0 ? 0.f : pow2c(e_beta - eb_nb);
+        inflow_prime<NC, 0>(sa, ina);
       }
+      {
+        int spos[NC / 2];  // class-sorted staging slot of my label cells
 #pragma unroll
-      for (int f = 0; f < FR; ++f) gb[f] = warp_sum_fx(gbl[f]);
-      float tot[FR];
+        for (int k = 0; k < NC / 2; ++k) spos[k] = tab[3 * (NC / 2) * 32 + k * 32 + lane];
+        for_frames<NC, 0>(pblk, f0, nh, la, blank_off, [&](int r, const FProbs<NC>& pc, auto&& mid) {
+          float* gf = rows + (r - f0) * RS;
+          const float2* src = reinterpret_cast<const float2*>(gf) + lane;
+          float2 w[NC / 2];
 #pragma unroll
-      for (int f = 0; f < FR; ++f) tot[f] = gbl[f];
+          for (int k = 0; k < NC / 2; ++k) w[k] = src[k * 32];
+          fstep<NC, 0, false>(sa, ina, la, pc, nullptr, mid);
+          __syncwarp();  // every lane has read the row before it becomes the staging area
+          float gb = 0.f;
+#pragma unroll
+          for (int k = 0; k < NC / 2; ++k) {
+            gb = fmaf(sa.x[2 * k], w[k].x, gb);
+            if (spos[k] >= 0) gf[spos[k]] = sa.x[2 * k + 1] * w[k].y;
+          }
+          gf[F_SPAD + lane] = gb;
+          if (lane == 0) gf[F_SPAD + 32] = 0.f;  // the always-zero slot out-of-range class reads are pointed at
+        });
+      }
+      __syncwarp();
+      fstamp(P, uiter, nmine, 4);
+      // ---- class sums of the staged posteriors and gradient rows of this half's frames, all interleaved.
+      // Staging is sorted by class, so a class is one contiguous range [cls[v], cls[v+1]): each lane adds up
+      // the ranges of its classes directly (independent loads, no scan).  The two warp-wide sums per frame (blank
+      // partials, total mass) go through the integer reduction unit in 2^-26 fixed point: one REDUX each
+      // instead of five dependent shuffle rounds.
+      constexpr int FR = F_FR;
 #pragma unroll 1
-      for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
-        const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
-        const int ml = (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
-        float acc[FR];
-#pragma unroll
-        for (int f = 0; f < FR; ++f) acc[f] = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < ml; ++k) {
-          const int idx = ca + k < cb ? ca + k : F_SPAD + 32;  // out of range: a slot that always holds zero
-#pragma unroll
-          for (int f = 0; f < FR; ++f) acc[f] += gfp[f][idx];
-        }
-        float pv[FR];
-#pragma unroll
-        for (int f = 0; f < FR; ++f) pv[f] = v < V ? pblk[v * F_KS + (f < nf ? r + f : r)] : 0.f;
+      for (int r0 = 0; r0 < nh; r0 += FR) {
+        const int nf = nh - r0 < FR ? nh - r0 : FR;
+        const float* gfp[FR];
+        float gbl[FR], gb[FR];
 #pragma unroll
         for (int f = 0; f < FR; ++f) {
-          tot[f] += acc[f];
-          const float gv = acc[f] + (v == P.blank ? gb[f] : 0.f);
-          if (f < nf && v < V) st_stream(g_base + (int64_t)(t0 + r + f) * P.st + v, (pv[f] - gv) * scale);
+          gfp[f] = rows + (r0 + (f < nf ? f : 0)) * RS;
+          gbl[f] = gfp[f][F_SPAD + lane];
+        }
+#pragma unroll
+        for (int f = 0; f < FR; ++f) gb[f] = warp_sum_fx(gbl[f]);
+        float tot[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) tot[f] = gbl[f];
+#pragma unroll 1
+        for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
+          const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
+          const int ml = (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
+          float acc[FR];
+#pragma unroll
+          for (int f = 0; f < FR; ++f) acc[f] = 0.f;
+#pragma unroll 2
+          for (int k = 0; k < ml; ++k) {
+            const int idx = ca + k < cb ? ca + k : F_SPAD + 32;  // out of range: a slot that always holds zero
+#pragma unroll
+            for (int f = 0; f < FR; ++f) acc[f] += gfp[f][idx];
+          }
+          float pv[FR];
+#pragma unroll
+          for (int f = 0; f < FR; ++f) pv[f] = v < V ? pblk[v * F_KS + f0 + r0 + (f < nf ? f : 0)] : 0.f;
+#pragma unroll
+          for (int f = 0; f < FR; ++f) {
+            tot[f] += acc[f];
+            const float gv = acc[f] + (v == P.blank ? gb[f] : 0.f);
+            if (f < nf && v < V) st_stream(g_base + (int64_t)(t0 + f0 + r0 + f) * P.st + v, (pv[f] - gv) * scale);
+          }
+        }
+        // D3: the posteriors of a frame sum to one unless mass was lost to fp32 range somewhere
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+          const float t = warp_sum_fx(tot[f]);
+          if (f < nf && !(fabsf(t - 1.f) <= F_MASS_TOL)) mass_ok = false;
         }
       }
-      // D3: the posteriors of a frame sum to one unless mass was lost to fp32 range somewhere
-#pragma unroll
-      for (int f = 0; f < FR; ++f) {
-        const float t = warp_sum_fx(tot[f]);
-        if (f < nf && !(fabsf(t - 1.f) <= F_MASS_TOL)) mass_ok = false;
-      }
+      __syncwarp();
     }
-    __syncwarp();
+    if (stop) break;
     i = i_next;
   }
   if (!mass_ok && lane == 0) atomicOr(&sc->uflag, 8);  // D3 (the sums are warp-uniform)
@@ -876,9 +913,10 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
 
   unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
   unsigned qbase = 0u, uiter = 0u, nraw = 0u;
-  // Warp w issues from sub-partition w % 4.  Two CTAs share an SM: the second one to arrive swaps its
-  // mains and loaders (warps 0,1 <-> 2,3), so that each sub-partition carries ONE main sweep, one loader
-  // and two workers instead of two mains on two of them.
+  // Warp w issues from sub-partition w % 4.  Two CTAs share an SM; the second one to arrive uses a mirrored role
+  // map, so that every sub-partition carries ONE main sweep instead of both CTAs' mains sitting on the same two:
+  //   8 warps:  rot 0: MF 0  MB 1  LF 2  LB 3  workers 4..7     rot 1: MF 2  MB 3  LF 0  LB 1  workers 4..7
+  //   10 warps: rot 0: MF 0  MB 1  LF 8  LB 9  workers 2..7     rot 1: MF 2  MB 3  LF 8  LB 9  workers 0,1,4..7
   if (tid == 0) {
 #ifdef SSD_EMU
     sc->rot = (int)(blockIdx.x & 1u);
@@ -889,7 +927,19 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
 #endif
   }
   __syncthreads();
-  const int rwarp = warp < 4 ? (warp ^ (sc->rot << 1)) : warp;  // role index: 0 MF, 1 MB, 2 LF, 3 LB, 4.. workers
+  int role;  // 0 MF, 1 MB, 2 LF, 3 LB, 4 + w: worker w
+  {
+    const int m0 = sc->rot ? 2 : 0;  // first main warp
+    if (F_W == 4) {
+      role = warp < 4 ? (warp ^ m0) : warp;
+    } else {
+      if (warp == m0) role = 0;
+      else if (warp == m0 + 1) role = 1;
+      else if (warp == 8) role = 2;
+      else if (warp == 9) role = 3;
+      else role = 4 + (warp < 4 ? (warp & 1) : warp - 2);  // the two free low warps are workers 0,1; warps 4..7 workers 2..5
+    }
+  }
 
   for (;;) {
     if (tid == 0) {
@@ -953,19 +1003,19 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
         for (int64_t r = pl.Tb + warp; r < P.T; r += F_THREADS / 32)
           for (int v = lane; v < P.V; v += 32) st_stream(g0 + r * P.st + v, 0.f);
       }
-      if (warp < 4) {
-        const int h = rwarp & 1;
+      if (role < 4) {
+        const int h = role & 1;
         MainView mv;
         mv.base = smem + M.main_off + (size_t)h * M.main_bytes;
         mv.bar = bars + h * FB_PER_MAIN;
         mv.p_slot = M.p_slot;
         mv.raw_slot = M.raw_slot;
-        if (rwarp == 0) fast_main<NC, 0>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
-        else if (rwarp == 1) fast_main<NC, 1>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
-        else if (rwarp == 2) fast_loader<0>(P, mv, pl, qbase, sc, uiter);
+        if (role == 0) fast_main<NC, 0>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
+        else if (role == 1) fast_main<NC, 1>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
+        else if (role == 2) fast_loader<0>(P, mv, pl, qbase, sc, uiter);
         else fast_loader<1>(P, mv, pl, qbase, sc, uiter);
       } else {
-        const int w = warp - 4;
+        const int w = role - 4;
         unsigned char* wb = smem + M.worker_off + (size_t)w * M.worker_bytes;
         WorkerView wv;
         wv.rows = reinterpret_cast<float*>(wb);
@@ -1029,7 +1079,7 @@ static bool fast_plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, FastPl
   pl.grid = (int)(B < slots ? B : slots);
   pl.ckpt_rec_bytes = (size_t)pl.NC * 32 * 4 + 128;
   pl.ckpt_cta_bytes = (size_t)2 * pl.nb_max * pl.ckpt_rec_bytes;
-  pl.ws_bytes = 256 + 4096 + (((size_t)B * 4 + 255) & ~(size_t)255) + (size_t)pl.grid * pl.ckpt_cta_bytes + (size_t)8 * F_TLOG_N * F_TLOG_S * 8;
+  pl.ws_bytes = 256 + 4096 + (((size_t)B * 4 + 255) & ~(size_t)255) + (size_t)pl.grid * pl.ckpt_cta_bytes + (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8;
   return true;
 }
 
@@ -1078,7 +1128,7 @@ int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t s
   P.RS = pl.RS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
   if (fast_env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;
-  P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)8 * F_TLOG_N * F_TLOG_S * 8) : nullptr;
+  P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8) : nullptr;
   *flags = P.flags;
   *nflag = P.counter + 1;
   switch (pl.NC) {

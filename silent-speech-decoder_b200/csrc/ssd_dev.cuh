@@ -103,11 +103,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // For waits that are expected to be long (a producer far ahead of its consumer, a worker waiting for
 // its first block): back off between polls so that the issue slots go to the warps with work.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 500u) {
 #ifdef SSD_EMU
+  (void)ns;
   emu::mbar_wait(bar, parity);
 #else
-  while (!mbar_test(bar, parity)) __nanosleep(200);
+  while (!mbar_test(bar, parity)) __nanosleep(ns);
 #endif
 }
 
