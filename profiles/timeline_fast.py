@@ -13,11 +13,11 @@ for _ in range(2):
 torch.cuda.synchronize()
 ws = ops._WS[(0, "loss")]
 N, S = 256, 6
-NW = 10
+NW = 8  # warps per CTA of the default worker shape (4 workers)
 log = ws[-NW * N * S * 8:].view(torch.int64).cpu().numpy().reshape(NW, N, S)
 t0 = log[:, :, :5][log[:, :, :5] > 0].min()
 print("utterance 0: S =", int(tl[0]), " cycles since first stamp")
-names = ["w0 MF", "w1 MB", "w2 W0", "w3 W1", "w4 W2", "w5 W3", "w6 W4", "w7 W5", "w8 LF", "w9 LB"]  # role map of an unrotated CTA
+names = ["MF", "MB", "LF", "LB", "W0", "W1", "W2", "W3"]  # role map of an unrotated CTA
 for w in range(NW):
     a = log[w]
     idx = np.where(a[:, 0] > 0)[0]
@@ -28,4 +28,4 @@ for w in range(NW):
     for i in sel:
         st = [int(v - t0) if v > 0 else -1 for v in a[i, :5]]
         d = [st[k + 1] - st[k] if st[k + 1] >= 0 and st[k] >= 0 else None for k in range(4)]
-        print(f"   ev {i:3d} q={a[i, 5] if 2 <= w <= 7 else '-'} stamps {st}  deltas {d}")
+        print(f"   ev {i:3d} q={a[i, 5] if w >= 4 else '-'} stamps {st}  deltas {d}")

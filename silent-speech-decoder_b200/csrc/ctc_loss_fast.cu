@@ -482,49 +482,45 @@ __device__ __forceinline__ int block_order(int i, int NB, int Tb) {
 
 // Convert one block of raw log-prob rows into a class-major probability block.  `raw` is the block in
 // shared memory ([n][V], TMA-loaded) or, if null, `graw` the same rows in global memory (row stride st).
-// Two (frame quad, class) items per lane and pass: eight independent load -> exp chains in flight.
+// One (frame quad, class) item per lane and pass: four independent load -> exp chains in flight, small code.
 // Returns non-zero if a value outside +-F_LP_ABS (or NaN) was seen (D1).
 template <bool SMEM>
 __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
                                                float* __restrict__ pblk) {
   const int lane = lane_id();
   float amax = 0.f;  // largest |log-prob| seen (a NaN passes here and poisons Z or a frame's mass instead)
-  for (int base = 0; base < 2 * V; base += 64) {
-    float lp[2][4];
-    int vv[2], hh[2];
+#pragma unroll 1
+  for (int base = 0; base < 2 * V; base += 32) {
+    int idx = base + lane;  // item = (frame quad, class): consecutive lanes, consecutive classes
+    const bool live = idx < 2 * V;
+    idx = live ? idx : 2 * V - 1;
+    const int hq = idx >= V ? 1 : 0;
+    const int v = idx - hq * V;
+    float lp[4], pr[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      int idx = base + 32 * u + lane;  // consecutive lanes, consecutive classes
-      idx = idx < 2 * V ? idx : 2 * V - 1;
-      hh[u] = idx >= V ? 1 : 0;
-      vv[u] = idx - hh[u] * V;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int r = hh[u] * 4 + j;
-        r = r < n ? r : n - 1;  // rows beyond a partial block: re-read the last one, masked below
-        lp[u][j] = SMEM ? raw[r * V + vv[u]] : ld_stream(graw + (int64_t)r * st + vv[u]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      int r = hq * 4 + j;
+      r = r < n ? r : n - 1;  // rows beyond a partial block: re-read the last one, masked below
+      lp[j] = SMEM ? raw[r * V + v] : ld_stream(graw + (int64_t)r * st + v);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float pr[4];
+    for (int j = 0; j < 4; ++j) {
+      amax = fmaxf(amax, fabsf(lp[j]));
+      const float pv = prob_f(lp[j]);
+      pr[j] = hq * 4 + j < n ? pv : 0.f;
+    }
+    if (live) {
+      float* dst = pblk + v * F_KS + hq * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        amax = fmaxf(amax, fabsf(lp[u][j]));
-        const float pv = prob_f(lp[u][j]);
-        pr[j] = hh[u] * 4 + j < n ? pv : 0.f;
-      }
-      if (base + 32 * u + lane < 2 * V) {
-        float* dst = pblk + vv[u] * F_KS + hh[u] * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = pr[j];
-      }
+      for (int j = 0; j < 4; ++j) dst[j] = pr[j];
     }
   }
   return amax > F_LP_ABS ? 1 : 0;
 }
-// one loop per source: the unused path's address arithmetic would otherwise ride along predicated off
-__device__ __forceinline__ int convert_block(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
+// one loop per source: the unused path's address arithmetic would otherwise ride along predicated off.
+// NOT inlined: loaders and workers then run one shared copy, which is what the instruction cache wants
+// (the kernel is instruction-fetch sensitive: four different roles issue from every sub-partition).
+__device__ __noinline__ int convert_block(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
                                              float* __restrict__ pblk) {
   return raw ? convert_block_t<true>(raw, graw, st, n, V, pblk) : convert_block_t<false>(raw, graw, st, n, V, pblk);
 }
@@ -561,7 +557,7 @@ __device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan
     const unsigned Q = qbase + (unsigned)bi;
     const int slot = (int)(Q % F_NP);
     fstamp(P, uiter, bi, 0);
-    mbar_wait_relaxed(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u);  // I am blocks ahead: no hurry
+    mbar_wait_relaxed(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u, 2000u);  // I am blocks ahead: no hurry
     fstamp(P, uiter, bi, 1);
     const int q = blk_of(bi);
     const int n = min(F_K, pl.Tb - q * F_K);
@@ -601,10 +597,13 @@ __device__ void fast_main(const FastParams& P, const MainView& mv, const FPlan& 
   Inflow in;
   inflow_prime<NC, DIR>(s, in);
   bool ok = true;
+  // the workers sleep on named barrier 1 (no polling) until both sweeps are about a block away from meeting
+  const int bi_wake = pl.NB / 2 > 1 ? pl.NB / 2 - 1 : 0;
   for (int bi = 0; bi < pl.NB; ++bi) {
     const int q = DIR ? pl.NB - 1 - bi : bi;
     const unsigned Q = qbase + (unsigned)bi;
     const int slot = (int)(Q % F_NP);
+    if (bi == bi_wake) bar_arrive(1, 32 * (F_W + 2));
     fstamp(P, uiter, bi, 0);
     mbar_wait(&mv.bar[FB_PFULL + slot], (Q / F_NP) & 1u);
     fstamp(P, uiter, bi, 1);
@@ -674,6 +673,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes);
     bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
   };
+  bar_sync(1, 32 * (F_W + 2));  // released by the two mains shortly before the first block can be ready
   int i = grab();
   if (i < nblk && P.use_tma && lane == 0) issue_raw(i, nraw);
   int nmine = 0;
@@ -718,7 +718,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
         load_labels<NC, 1>(lb, tab);
         Inflow in;
         inflow_prime<NC, 1>(s, in);
-        if (f0 + nh < n)
+        if (F_H < F_K && f0 + nh < n)
           for_frames<NC, 1>(pblk, f0 + nh, n - f0 - nh, lb, blank_off,
                             [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, 1, false>(s, in, lb, pc, nullptr, mid); });
         for_frames<NC, 1>(pblk, f0, nh, lb, blank_off, [&](int r, const FProbs<NC>& pc, auto&& mid) {

@@ -43,6 +43,15 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 #endif
 }
 
+// bar.arrive id, n : count towards barrier `id` without waiting (the waiters use bar_sync with the same n)
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+#ifdef SSD_EMU
+  emu::bar_arrive(id, nthreads);
+#else
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 // ------------------------------------------------------------------ mbarrier
 #ifndef SSD_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -252,6 +252,15 @@ inline void bar_sync(int id, int count) {
   yield_until([bp, g] { return bp->gen != g; }, "bar.sync", bp);
 }
 
+// bar.arrive: counts like bar.sync but does not wait
+inline void bar_arrive(int id, int count) {
+  NamedBar& b = S().bars[id];
+  if (++b.arrived == count) {
+    b.arrived = 0;
+    ++b.gen;
+  }
+}
+
 inline int lane_id() { return S().cur->linear & 31; }
 inline int warp_id() { return S().cur->linear >> 5; }
 
@@ -335,6 +344,7 @@ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __restrict__ __restrict

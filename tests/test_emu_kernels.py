@@ -68,6 +68,61 @@ def test_loss_wide_lattice_and_extreme_range(lib):
         assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
 
 
+def test_loss_fast_path_flags_and_fallback(lib):
+    """The fp32 fast path checks its own result per utterance; what it flags is recomputed by the fp64 kernel.
+    Flags (FastParams::flags): 0 fast result kept, 1 not covered, 2 log-prob range, 4 non-finite strip,
+    8 posterior mass, 16 Z."""
+    # plain utterances stay on the fast path and meet the tolerance on their own
+    lp = synth.flat(3, 200, 41)
+    tg, tl = synth.targets(3, 60, 42)
+    il = torch.tensor([200, 150, 97])
+    nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=3, with_fallbacks="flags")
+    assert flags.tolist() == [0, 0, 0]
+    n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+    assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
+    # rows the fast path must hand over: no frames, infeasible (S > T), a log-prob below the exp range
+    lp = synth.flat(5, 40, 43).clone()
+    tg, tl = synth.targets(5, 12, 44)
+    il = torch.tensor([40, 0, 5, 40, 40])
+    tl[:] = torch.tensor([12, 3, 12, 6, 6])
+    lp[3, 7, 2] = -95.0
+    lp[4, 9, 5] = -120.0
+    nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=5, with_fallbacks="flags")
+    assert flags[0] == 0 and flags[1] == 1 and (flags[2] & 16) and (flags[3] & 2) and (flags[4] & 2)
+    n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5, atol=1e-6)
+    assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
+    # confident posteriors that disagree with the target: cells of one lane thousands of binades apart.
+    # fp32 loses mass there, the per-frame mass check sees it (flag 8), the fp64 kernel delivers the result
+    lp = synth.peaked(2, 700, 77, boost=10.0)
+    tg, tl = synth.targets(2, 120, 18)
+    tl[:] = 120
+    il = torch.tensor([700, 700])
+    nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=2, with_fallbacks="flags")
+    assert (flags & 8).any()
+    n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+    assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
+
+
+def test_loss_fast_path_partial_blocks_and_forward_only(lib):
+    # input lengths around the 8-frame block size, odd lengths, one label, forward only
+    for T in (1, 2, 7, 8, 9, 15, 17, 31):
+        lp = synth.flat(2, T, 300 + T)
+        S = max(1, min(6, T // 2))
+        tg, tl = synth.targets(2, S, 5 + T)
+        tl[:] = torch.tensor([S, max(1, S // 2)])
+        il = torch.tensor([T, max(1, T - 1)])
+        nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=2, with_fallbacks="flags")
+        n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+        np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5, atol=1e-6)
+        assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item() + 1e-12, T
+        fwd, none = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, want_grad=False)
+        assert none is None
+        np.testing.assert_allclose(fwd, n64.numpy(), rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("order", ["rev", "rnd:3", "rnd:8"])
 def test_schedule_independence(order):
     """Same results when the emulator visits threads in another order (separate process: the

@@ -76,6 +76,40 @@ def test_vs_fp64_oracle(gen, B, T, S):
     _check(lp, il, tg, tl)
 
 
+def test_fast_path_and_exact_fallback(monkeypatch):
+    """ssd_ctc_loss = fp32 fast kernel + fp64 kernel over what the fast one flags.  Plain batches stay on the fast
+    path; confident-but-wrong posteriors lose fp32 mass, are caught by the per-frame mass check and come back
+    from the exact kernel; both meet the same tolerance.  SSD_LOSS_EXACT=1 forces the fp64 kernel alone."""
+    lp = synth.flat(32, 400, 11)
+    tg, tl = synth.targets(32, 100, 12)
+    il = synth.ragged_lengths(32, 400, 13)
+    _check(lp, il, tg, tl)
+    assert ops.loss_fallback_count(32, 400, 48, 100) == 0
+    lp = synth.peaked(8, 700, 77, boost=10.0)
+    tg, tl = synth.targets(8, 120, 18)
+    tl[:] = 120
+    il = torch.full((8,), 700)
+    _check(lp, il, tg, tl)
+    assert ops.loss_fallback_count(8, 700, 48, 120) > 0
+    # same inputs, exact kernel only: identical answers within the tolerance of either path
+    nll_a, g_a = ops.ctc_loss_fwd_bwd(lp.cuda(), il, tg, tl, blank=1, mean_denominator=8)
+    monkeypatch.setenv("SSD_LOSS_EXACT", "1")
+    nll_b, g_b = ops.ctc_loss_fwd_bwd(lp.cuda(), il, tg, tl, blank=1, mean_denominator=8)
+    assert ops.loss_fallback_count(8, 700, 48, 120) is None
+    assert ((nll_a - nll_b).abs() / nll_b.abs()).max().item() < 1e-6
+    assert (g_a - g_b).abs().max().item() <= 1e-5 * g_b.abs().max().item()
+
+
+def test_fast_path_flags_out_of_range_inputs():
+    lp = synth.flat(4, 64, 21).clone()
+    tg, tl = synth.targets(4, 10, 22)
+    il = torch.tensor([64, 64, 0, 7])
+    tl[3] = 10                      # infeasible: 10 labels in 7 frames
+    lp[1, 5, 3] = -200.0            # exp underflows in fp32
+    _check(lp, il, tg, tl)
+    assert ops.loss_fallback_count(4, 64, 48, 10) == 3
+
+
 def test_edge_rows_and_flags():
     lp = synth.flat(6, 30, 77)
     tg, tl = synth.targets(6, 12, 78)
