@@ -59,6 +59,9 @@ constexpr int F_NRAW = 3;  // raw-row ring depth per main
 #ifndef SSD_F_FR
 #define SSD_F_FR 4
 #endif
+#ifndef SSD_F_PAIR
+#define SSD_F_PAIR 1  // frame loops: 1 = two steps per trip with alternating probability registers, 0 = one step per trip
+#endif
 constexpr int F_FR = SSD_F_FR;  // frames interleaved in the gradient stage
 constexpr int F_TOP = 40;  // renormalised strips have their largest cell in [2^40, 2^41)
 constexpr int F_SPAD = 256;  // label staging capacity (S <= 255 on this path)
@@ -289,6 +292,7 @@ __device__ __forceinline__ void for_frames(const float* pblk, int f0, int n, con
   pp.blank = sadd(base, blank_off);
 #pragma unroll
   for (int k = 0; k < NC / 2; ++k) pp.lab[k] = sadd(base, lt.off[k]);
+#if SSD_F_PAIR
   FProbs<NC> A, B;
   load_probs<NC, 0>(A, pp);
 #pragma unroll 1
@@ -311,6 +315,25 @@ __device__ __forceinline__ void for_frames(const float* pblk, int f0, int n, con
       });
     }
   }
+#else
+  // one step per trip: half the code of the two-set version at the price of NC/2+1 register moves per step
+  FProbs<NC> A;
+  load_probs<NC, 0>(A, pp);
+#pragma unroll 1
+  for (int rr = 0; rr < n; ++rr) {
+    const int r = DIR ? f0 + n - 1 - rr : f0 + rr;
+    FProbs<NC> B;
+    body(r, A, [&]() {
+      if (rr + 1 < n) {
+        pp.blank = sadd(pp.blank, D);
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) pp.lab[k] = sadd(pp.lab[k], D);
+        load_probs<NC, 0>(B, pp);
+      }
+    });
+    A = B;
+  }
+#endif
 }
 
 // One frame of the recursion.  DIR 0 (alpha): cell s pulls from s-1 and, label cells with a different
