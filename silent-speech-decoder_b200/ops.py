@@ -166,11 +166,19 @@ def ctc_loss_fwd_bwd(
             sb, st = _strides(x)
             nbytes = int(lib.ssd_ctc_loss_workspace_bytes(B, T, V, S))
             ws = _workspace(dev, "loss", nbytes)
+            # ragged batches with host-resident lengths (what the reference passes, losses.py:55): longest utterances
+            # first, so that the CTAs that start last get the short ones.  Device-resident lengths are not inspected
+            # (no sync, no extra launches on the training step).
+            order = None
+            hl = torch.as_tensor(input_lengths)
+            if B > 1 and not hl.is_cuda and int(hl.min()) != int(hl.max()):
+                order = torch.argsort(hl.reshape(-1), descending=True, stable=True).to(torch.int32).to(dev)
             gm = None
             if grad_mul is not None:
                 gm = grad_mul.detach().to(device=dev, dtype=torch.float32).reshape(1)
             lib.check(lib.ssd_ctc_loss(x.data_ptr(), B, T, V, sb, st, tg.data_ptr() if S else None,
-                                       tg.stride(0) if (S and B > 1) else max(S, 1), S, il.data_ptr(), tl.data_ptr(), None,
+                                       tg.stride(0) if (S and B > 1) else max(S, 1), S, il.data_ptr(), tl.data_ptr(),
+                                       order.data_ptr() if order is not None else None,
                                        int(blank), int(bool(zero_infinity)), int(mean_denominator),
                                        gm.data_ptr() if gm is not None else None, nll.data_ptr(),
                                        grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
