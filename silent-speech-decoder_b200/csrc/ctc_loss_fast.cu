@@ -196,7 +196,10 @@ struct FastScal {
 template <int NC>
 struct FStrip {
   float x[NC];
-  float fin;  // 2^(neighbour e - my e): brings the neighbour's boundary cells into my basis
+  // 2^(neighbour e - my e) as a product of two powers of two: brings the neighbour's boundary cells into my basis.
+  // One float cannot hold it: adjacent lanes of a short, steep lattice differ by more than 2^126 while the
+  // boundary cell times the factor is still a normal number (and 3 % of its neighbour cell, not noise).
+  float fin, fin2;
   int e;
 };
 
@@ -258,7 +261,10 @@ struct FProbs {  // one frame
 typedef const char* saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const void* p) { return reinterpret_cast<const char*>(p); }
 template <int IMM>
-__device__ __forceinline__ float lds_pinned(saddr_t a) { return *reinterpret_cast<const float*>(a + IMM); }
+__device__ __forceinline__ float lds_pinned(saddr_t a) {
+  SSD_ASSERT((const unsigned char*)(a + IMM) >= emu::dyn_smem() && (const unsigned char*)(a + IMM) + 4 <= emu::dyn_smem() + emu::dyn_smem_size());
+  return *reinterpret_cast<const float*>(a + IMM);
+}
 __device__ __forceinline__ saddr_t sadd(saddr_t a, int d) { return a + d; }
 #else
 typedef uint32_t saddr_t;
@@ -385,7 +391,7 @@ __device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<N
     mid();
 #pragma unroll
     for (int i = NC - 2; i >= 2; --i) cell(i, x[i - 1], x[i - 2]);
-    const float n1 = in.a * s.fin;  // lane 0: fin = 0
+    const float n1 = in.a * s.fin * s.fin2;  // lane 0: fin = 0
     cell(1, x[0], n1);
     cell(0, n1, 0.f);
   } else {
@@ -397,19 +403,32 @@ __device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<N
     mid();
 #pragma unroll
     for (int i = 2; i < NC - 1; ++i) cell(i, x[i + 1], x[i + 2 < NC ? i + 2 : NC - 1]);
-    const float m0 = in.a * s.fin, m1 = in.b * s.fin;  // lane 31: fin = 0
+    const float m0 = in.a * s.fin * s.fin2, m1 = in.b * s.fin * s.fin2;  // lane 31: fin = 0
     cell(NC - 1, m0, m1);
   }
   in = nxt;
 }
 
+// how much of a lane's posterior scale 2^qe the alpha side takes (the beta~ side takes the rest): half, but no more
+// than either side can hold next to values of up to 2^(TOP+14)
+__device__ __forceinline__ int scale_split(int qe) {
+  int h = qe >> 1;
+  const int cap = 126 - (F_TOP + 14);
+  h = h < qe - cap ? qe - cap : h;
+  return h > cap ? cap : h;
+}
+
 // the boundary factor both the mains and the workers derive from the lane exponents
-template <int DIR>
-__device__ __forceinline__ float fin_of(int e_me) {
+template <int NC, int DIR>
+__device__ __forceinline__ void set_fin(FStrip<NC>& s, int e_me) {
   const int lane = lane_id();
   const int e_nb = DIR == 0 ? __shfl_up_sync(FULL, e_me, 1) : __shfl_down_sync(FULL, e_me, 1);
   const bool edge = DIR == 0 ? lane == 0 : lane == 31;
-  return edge ? 0.f : pow2c(e_nb - e_me);
+  int d = e_nb - e_me;
+  d = d < -252 ? -252 : (d > 252 ? 252 : d);
+  const int d1 = d >> 1;
+  s.fin = edge ? 0.f : pow2c(d1);
+  s.fin2 = pow2c(d - d1);
 }
 
 // Block boundary: bring my largest cell to [2^TOP, 2^(TOP+1)), agree on exponents with the
@@ -452,7 +471,7 @@ __device__ __forceinline__ bool renorm_exchange(FStrip<NC>& s) {
     for (int i = 0; i < NC; ++i) s.x[i] *= g;
     s.e = e_nb;
   }
-  s.fin = fin_of<DIR>(s.e);
+  set_fin<NC, DIR>(s, s.e);
   return ok;
 }
 
@@ -464,6 +483,7 @@ __device__ __forceinline__ void sweep_init_f(int L, FStrip<NC>& s) {
   for (int i = 0; i < NC; ++i) s.x[i] = (lane * NC + i == c0) ? 1.f : 0.f;
   s.e = 0;
   s.fin = (DIR == 0 ? lane == 0 : lane == 31) ? 0.f : 1.f;
+  s.fin2 = 1.f;
 }
 
 // checkpoint record: [NC][32] cells, [32] exponents; lanes beyond the lattice hold zeros and are skipped
@@ -725,8 +745,11 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     // ---- the block in halves of F_H frames (lower half first: alpha runs upwards through both)
     FStrip<NC> sa;  // alpha state, carried from the lower half into the upper
     Inflow ina;
-    int e_alpha = 0, e_beta = 0;
+    int e_alpha = 0, e_beta = 0, g_beta = 0;
     bool stop = false;
+    // every block but the first needs Z before its sweeps (they run pre-scaled); the first one computes it
+    bool z_known = i != 0;
+    if (z_known && want_grad) mbar_wait_relaxed(z_ready, uiter & 1u);
 #pragma unroll 1
     for (int f0 = 0; f0 < n; f0 += F_H) {
       const int nh = min(F_H, n - f0);
@@ -736,7 +759,20 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
         FStrip<NC> s;
         ckpt_load<NC>(ck_b + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
         e_beta = s.e;
-        s.fin = fin_of<1>(s.e);
+        if (f0 == 0) e_alpha = ld_cg(reinterpret_cast<const int*>(ck_a + (size_t)q * P.ckpt_rec_bytes + (size_t)NC * 32 * 4) + lane);
+        if (z_known) {
+          // posterior = alpha * beta~ * 2^(e_a + e_b - e_Z) / Zm.  The scale is SPLIT between the two recomputed sweeps
+          // (alpha takes 2^h, beta~ takes 2^(qe - h) / Zm): either factor alone can leave the fp32 range when the two
+          // sweeps have steep opposite slopes inside a lane, their product at a cell never does (it is a posterior).
+          const int qe = e_alpha + e_beta - sc->ez;
+          g_beta = qe - scale_split(qe);
+          const float c = pow2c(g_beta) * sc->inv_zm;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) s.x[k] *= c;
+        } else {
+          g_beta = 0;
+        }
+        set_fin<NC, 1>(s, s.e - g_beta);
         FLabels<NC> lb;
         load_labels<NC, 1>(lb, tab);
         Inflow in;
@@ -759,11 +795,10 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
       load_labels<NC, 0>(la, tab);
       if (f0 == 0) {
         ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, sa, pl.L);
-        e_alpha = sa.e;
-        if (i == 0) {
+        if (!z_known) {
           // Z = sum over the lattice of alpha_t * beta~_t at the block's first frame (unscaled pass)
           FStrip<NC> z = sa;
-          z.fin = fin_of<0>(z.e);
+          set_fin<NC, 0>(z, z.e);
           Inflow zin;
           inflow_prime<NC, 0>(z, zin);
           FProbs<NC> pc;
@@ -812,14 +847,31 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
           stop = true;
           break;
         }
-        mbar_wait_relaxed(z_ready, uiter & 1u);
-        // run alpha pre-scaled by c = 2^(e_alpha + e_beta - eZ) / Zm: the products below are posteriors
-        const float c = pow2c(e_alpha + e_beta - sc->ez) * sc->inv_zm;
+        const int qe = e_alpha + e_beta - sc->ez;
+        const int h = scale_split(qe);
+        if (!z_known) {
+          // the first block's rows were stored unscaled: give them their share of the scale now (my own cells)
+          z_known = true;
+          g_beta = qe - h;
+          const float c = pow2c(g_beta) * sc->inv_zm;
+#pragma unroll 1
+          for (int r = 0; r < nh; ++r) {
+            float2* row = reinterpret_cast<float2*>(rows + r * RS) + lane;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) sa.x[k] *= c;
-        // inflow = x_nb * 2^(ea_nb - ea_me) * c_me / c_nb = x_nb * 2^(eb_me - eb_nb)
-        const int eb_nb = __shfl_up_sync(FULL, e_beta, 1);
-        sa.fin = lane == 0 ? 0.f : pow2c(e_beta - eb_nb);
+            for (int k = 0; k < NC / 2; ++k) {
+              float2 w = row[k * 32];
+              w.x *= c;
+              w.y *= c;
+              row[k * 32] = w;
+            }
+          }
+        }
+        {
+          const float c = pow2c(h);
+#pragma unroll
+          for (int k = 0; k < NC; ++k) sa.x[k] *= c;
+        }
+        set_fin<NC, 0>(sa, e_alpha - h);
         inflow_prime<NC, 0>(sa, ina);
       }
       {
@@ -1092,6 +1144,10 @@ static bool fast_plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, FastPl
   for (int i = 0; i < 4 && !pl.NC; ++i)
     if (need <= buckets[i]) pl.NC = buckets[i];
   if (need <= 14 && need > 12) pl.NC = 14;
+  {  // tuning knob: force a wider strip than the lattice needs
+    const int nc = fast_env_int("SSD_LOSS_NC", 0);
+    if (nc >= pl.NC && (nc == 4 || nc == 8 || nc == 12 || nc == 14 || nc == 16)) pl.NC = nc;
+  }
   if (!pl.NC) return false;
   const int cells = 32 * pl.NC, stage = F_SPAD + 32 + 4;
   pl.RS = ((cells > stage ? cells : stage) + 3) & ~3;

@@ -231,6 +231,7 @@ inline void launch(dim3e grid, dim3e block, size_t smem, std::function<void()> b
       }
 }
 
+inline size_t dyn_smem_size() { return S().dyn_smem.size() - 1024; }
 inline unsigned char* dyn_smem() {
   State& s = S();
   uintptr_t p = (uintptr_t)s.dyn_smem.data();

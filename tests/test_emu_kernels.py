@@ -106,6 +106,24 @@ def test_loss_fast_path_flags_and_fallback(lib):
     assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
 
 
+def test_loss_fast_path_short_targets_in_a_wide_strip(lib):
+    """The strip width is chosen per launch from the longest target, so short targets share it: few live lanes, steep
+    opposite alpha / beta slopes inside a lane, lane exponents more than 2^126 apart.  These must stay correct (the
+    boundary factor is a product of two floats, the posterior scale is split between the two recomputed sweeps) and
+    whatever fp32 cannot hold must be flagged, never returned."""
+    B, T, S, V = 6, 600, 200, 48
+    g = torch.Generator().manual_seed(5)
+    tl = torch.tensor([200, 15, 22, 40, 17, 60])
+    tg = torch.randint(2, V, (B, S), generator=g, dtype=torch.int64) * (torch.arange(S)[None, :] < tl[:, None])
+    il = torch.full((B,), T, dtype=torch.int64)
+    lp = synth.flat(B, T, 7, V)
+    nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=B, with_fallbacks="flags")
+    n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+    assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
+    assert flags[0] == 0 and flags[5] == 0 and flags[3] == 0
+
+
 def test_loss_fast_path_partial_blocks_and_forward_only(lib):
     # input lengths around the 8-frame block size, odd lengths, one label, forward only
     for T in (1, 2, 7, 8, 9, 15, 17, 31):
