@@ -135,6 +135,7 @@ struct FastParams {
   int nb_max;
   int RS;  // worker row stride in floats
   int use_tma;
+  int rotate;  // 1: the second CTA of an SM mirrors its role map (tuning knob SSD_LOSS_NOROT)
   long long* tlog;  // SSD_LOSS_DBG & 8: [F_THREADS/32 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
 };
 constexpr int F_TLOG_N = 256, F_TLOG_S = 6;
@@ -998,7 +999,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
 #else
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    sc->rot = (int)(atomicAdd(P.sm_slot + smid, 1u) & 1u);
+    sc->rot = (int)(atomicAdd(P.sm_slot + smid, 1u) & 1u) & P.rotate;
 #endif
   }
   __syncthreads();
@@ -1207,6 +1208,7 @@ int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t s
   P.RS = pl.RS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
   if (fast_env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;
+  P.rotate = fast_env_int("SSD_LOSS_NOROT", 0) ? 0 : 1;
   P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8) : nullptr;
   *flags = P.flags;
   *nflag = P.counter + 1;
