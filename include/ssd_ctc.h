@@ -9,6 +9,10 @@
  *   src/decoding/ctc.py:75-96  pad->blank merge, label permutation, per-utterance
  *                              pyctcdecode decoder.decode(lp, beam_width, beam_prune_logp) -> ssd_ctc_beam
  *
+ * and, for the evaluation loop around the decoder (the first "next" row of the scope table),
+ *
+ *   src/evaluation/evaluate.py:34-38,61-83  jiwer.wer / jiwer.cer and _levenshtein_counts -> ssd_edit_counts
+ *
  * Conventions
  *   - All data pointers are DEVICE pointers (HBM).  The library never allocates, frees or
  *     retains device memory: the caller owns every buffer, including the workspace.
@@ -47,6 +51,7 @@ enum {
 #define SSD_MAX_VOCAB 128      /* V */
 #define SSD_MAX_TARGET 511     /* S: extended length 2S+1 <= 1023 lanes of the alpha/beta recursion */
 #define SSD_MAX_BEAM 512       /* beam_width */
+#define SSD_MAX_EDIT_LEN 8191  /* tokens per sequence in ssd_edit_counts */
 
 int ssd_abi_version(void);
 const char* ssd_last_error(void);
@@ -113,6 +118,19 @@ int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
                  const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
                  int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Levenshtein alignment counts of N (reference, hypothesis) token sequences: the arithmetic of
+ * jiwer.wer / jiwer.cer (src/evaluation/evaluate.py:34-38) and of the in-tree fallback
+ * `_levenshtein_counts` (evaluate.py:61-83) -- fewest edits, and among the alignments with the
+ * fewest edits the one with the most hits.  Tokens are words (WER) or characters (CER) mapped to
+ * non-negative int32 ids by the caller; sequences are concatenated, CSR style.
+ *   ref_tok / hyp_tok  int32 ids >= 0          ref_off / hyp_off  [N+1] int64 offsets, off[0] = 0
+ *   max_ref_len / max_hyp_len  upper bounds of the sequence lengths (<= SSD_MAX_EDIT_LEN)
+ *   counts             [N,4] int32: substitutions, deletions, insertions, hits
+ */
+int ssd_edit_counts(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* hyp_tok, const int64_t* hyp_off,
+                    int64_t N, int64_t max_ref_len, int64_t max_hyp_len, int32_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,9 +69,69 @@ def loss_cases():
     return cases
 
 
+def edit_pairs():
+    """Seeded (reference, hypothesis) sentence pairs: a small word list so hits and ties are common,
+    plus the edge cases (empty sides, identical, repeated words, all different)."""
+    import random
+
+    rng = random.Random(2301)
+    words = ["the", "a", "cat", "sat", "on", "mat", "dog", "ran", "to", "home", "and", "then", "it", "was", "so"]
+    pairs = [("", ""), ("", "a cat"), ("the cat sat", ""), ("the cat sat", "the cat sat"), ("a a a a", "a a"),
+             ("a b a b a b", "b a b a b a"), ("the  cat   sat ", " the cat sat"), ("x y z", "p q r s")]
+    for n in [1, 2, 3, 5, 8, 13, 21, 34, 60]:
+        for _ in range(4):
+            ref = [rng.choice(words) for _ in range(n)]
+            hyp = []
+            for w in ref:  # a noisy copy: substitutions, deletions, insertions
+                u = rng.random()
+                if u < 0.15:
+                    hyp.append(rng.choice(words))
+                elif u < 0.27:
+                    continue
+                else:
+                    hyp.append(w)
+                if rng.random() < 0.12:
+                    hyp.append(rng.choice(words))
+            pairs.append((" ".join(ref), " ".join(hyp)))
+    for _ in range(6):  # unrelated sequences of different lengths
+        pairs.append((" ".join(rng.choice(words) for _ in range(rng.randint(1, 40))),
+                      " ".join(rng.choice(words) for _ in range(rng.randint(1, 40)))))
+    return pairs
+
+
+def edit_golden() -> None:
+    """Word-level alignment counts from the reference's own `compute_error_breakdown`
+    (src/evaluation/evaluate.py:41-99).  jiwer is not installed; a stub module without
+    `compute_measures` makes the reference take its in-tree Levenshtein branch (:61-99), which is
+    the code this fixture pins.  Character-level counts run the same function over character lists
+    joined by spaces (one character per "word")."""
+    import json
+    import types
+
+    sys.modules.setdefault("jiwer", types.ModuleType("jiwer"))
+    from src.evaluation.evaluate import compute_error_breakdown
+
+    rows = []
+    for ref, hyp in edit_pairs():
+        w = compute_error_breakdown([ref], [hyp])
+        cr, ch = " ".join(ref.strip().replace(" ", "_")), " ".join(hyp.strip().replace(" ", "_"))
+        c = compute_error_breakdown([cr], [ch])
+        rows.append({"ref": ref, "hyp": hyp,
+                     "word": [int(w[k]) for k in ("substitutions", "deletions", "insertions", "hits")],
+                     "char": [int(c[k]) for k in ("substitutions", "deletions", "insertions", "hits")]})
+    refs, hyps = [r for r, _ in edit_pairs()], [h for _, h in edit_pairs()]
+    total = compute_error_breakdown(refs, hyps)
+    with open(os.path.join(OUT, "edit_ref.json"), "w") as f:
+        json.dump({"pairs": rows, "corpus_breakdown": total}, f, indent=0)
+    print("edit_ref.json", len(rows), "pairs")
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
+    if sys.argv[1:] == ["edit"]:
+        return edit_golden()
+    edit_golden()
     from src.decoding.ctc import _greedy_decode, build_greedy_decoder
     from src.data.vocab import Vocab as RefVocab
 

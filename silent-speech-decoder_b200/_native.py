@@ -25,6 +25,7 @@ SIGNATURES = {
     "ssd_ctc_beam": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _F32, _I32, _F32, _F32, _P, _P, _P, _P, _SZ, _P]),
     "ssd_ctc_loss_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_ctc_loss_fallback_counter_offset": (_SZ, [_I64, _I64, _I64, _I64]),
+    "ssd_edit_counts": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "ssd_ctc_loss": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
 }
 

@@ -83,4 +83,17 @@ int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
                      zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int ssd_edit_counts(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* hyp_tok, const int64_t* hyp_off,
+                    int64_t N, int64_t max_ref_len, int64_t max_hyp_len, int32_t* counts, void* stream) {
+  if (N < 0) return fail(SSD_ERR_BAD_ARG, "ssd_edit_counts: N=%lld < 0", (long long)N);
+  if (N > 0 && (!ref_off || !hyp_off || !counts)) return fail(SSD_ERR_BAD_ARG, "ssd_edit_counts: NULL offsets/counts pointer");
+  if (max_ref_len < 0 || max_hyp_len < 0) return fail(SSD_ERR_BAD_ARG, "ssd_edit_counts: negative length bound");
+  if (max_ref_len > SSD_MAX_EDIT_LEN || max_hyp_len > SSD_MAX_EDIT_LEN)
+    return fail(SSD_ERR_UNSUPPORTED, "ssd_edit_counts: sequences of %lld / %lld tokens exceed SSD_MAX_EDIT_LEN=%d",
+                (long long)max_ref_len, (long long)max_hyp_len, SSD_MAX_EDIT_LEN);
+  if (N > 0 && ((max_ref_len > 0 && !ref_tok) || (max_hyp_len > 0 && !hyp_tok))) return fail(SSD_ERR_BAD_ARG, "ssd_edit_counts: NULL token pointer");
+  if (N > 2147483647LL * 4) return fail(SSD_ERR_UNSUPPORTED, "ssd_edit_counts: N exceeds the grid range");
+  return edit_launch(ref_tok, ref_off, hyp_tok, hyp_off, N, max_ref_len, max_hyp_len, counts, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -43,4 +43,7 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
                 int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
                 size_t ws_bytes, cudaStream_t stream);
 
+int edit_launch(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* hyp_tok, const int64_t* hyp_off, int64_t N,
+                int64_t max_ref_len, int64_t max_hyp_len, int32_t* counts, cudaStream_t stream);
+
 }  // namespace ssd

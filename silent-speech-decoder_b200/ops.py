@@ -1,4 +1,4 @@
-"""Torch-facing launchers for the three kernels.
+"""Torch-facing launchers for the kernels.
 
 PyTorch is used here for device memory, streams and dtype plumbing only; all
 arithmetic happens inside libssd_ctc.so.  Inputs may live on the host (the
@@ -16,7 +16,7 @@ import torch
 from . import _native
 
 _WS: Dict[Tuple[int, str], torch.Tensor] = {}
-LAUNCHES = {"greedy": 0, "beam": 0, "loss": 0}  # kernels launched by this process (bench reads it)
+LAUNCHES = {"greedy": 0, "beam": 0, "loss": 0, "edit": 0}  # kernels launched by this process (bench reads it)
 
 
 def _device(t: torch.Tensor) -> torch.device:
@@ -204,3 +204,26 @@ def loss_fallback_count(B: int, T: int, V: int, S: int, device=None) -> Optional
     if ws is None or ws.numel() < off + 4:
         return None
     return int(ws[off:off + 4].view(torch.int32).item())
+
+
+def edit_counts(ref_tok: torch.Tensor, ref_off: torch.Tensor, hyp_tok: torch.Tensor, hyp_off: torch.Tensor,
+                max_ref_len: int, max_hyp_len: int) -> torch.Tensor:
+    """Levenshtein alignment counts of N token-sequence pairs given CSR style (int32 ids >= 0, int64 offsets
+    of N+1 entries). -> int32 (N,4) on the device: substitutions, deletions, insertions, hits."""
+    lib = _native.load()
+    dev = _device(ref_tok)
+    with torch.cuda.device(dev):
+        rt = ref_tok.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        ht = hyp_tok.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        ro = ref_off.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        ho = hyp_off.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        N = ro.numel() - 1
+        if N < 0 or ho.numel() != N + 1:
+            raise ValueError(f"offset arrays must both have N+1 entries; got {ro.numel()} and {ho.numel()}")
+        out = torch.zeros((N, 4), dtype=torch.int32, device=dev)
+        if N:
+            lib.check(lib.ssd_edit_counts(rt.data_ptr() if rt.numel() else None, ro.data_ptr(),
+                                          ht.data_ptr() if ht.numel() else None, ho.data_ptr(), N, int(max_ref_len),
+                                          int(max_hyp_len), out.data_ptr(), _stream_ptr(dev)))
+            LAUNCHES["edit"] += 1
+    return out

@@ -19,7 +19,7 @@ REPO = HERE.parent.parent
 CSRC = REPO / "silent-speech-decoder_b200" / "csrc"
 OUT = HERE / "_build"
 LIB = OUT / "libssd_ctc_emu.so"
-SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "capi.cu"]
+SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "capi.cu"]
 
 
 def build(force: bool = False) -> Path:
@@ -103,3 +103,16 @@ def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity
             return nll, grad, None if nfb is None else ws.view(np.int32)[(off - 4 + 256) // 4:(off - 4 + 256) // 4 + B].copy()
         return nll, grad, nfb
     return nll, grad
+
+
+def edit_counts(lib, refs, hyps):
+    """refs / hyps: lists of int sequences. -> (N,4) int32 [sub, del, ins, hits]."""
+    N = len(refs)
+    ro = np.zeros(N + 1, dtype=np.int64); ho = np.zeros(N + 1, dtype=np.int64)
+    ro[1:] = np.cumsum([len(r) for r in refs]); ho[1:] = np.cumsum([len(h) for h in hyps])
+    rt = np.array([x for r in refs for x in r] or [0], dtype=np.int32)
+    ht = np.array([x for h in hyps for x in h] or [0], dtype=np.int32)
+    out = np.full((max(N, 1), 4), -7, dtype=np.int32)
+    lib.check(lib.ssd_edit_counts(_ptr(rt), _ptr(ro), _ptr(ht), _ptr(ho), N, max((len(r) for r in refs), default=0),
+                                  max((len(h) for h in hyps), default=0), _ptr(out), None))
+    return out[:N]

@@ -12,6 +12,7 @@ import torch
 
 from oracle import beam as ob
 from oracle import ctc_loss as ol
+from oracle import edit as oe
 from oracle import greedy as og
 from silent_speech_decoder_b200 import synth
 from silent_speech_decoder_b200.data.vocab import Vocab
@@ -166,3 +167,37 @@ def test_schedule_independence(order):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
     assert outs[0] == outs[1]
+
+
+def _edit_vec(r, h):
+    c = oe.levenshtein_counts(list(r), list(h))
+    return [c["substitutions"], c["deletions"], c["insertions"], c["hits"]]
+
+
+def test_edit_counts_golden_and_edges(lib, golden_dir):
+    import json
+
+    z = json.load(open(os.path.join(golden_dir, "edit_ref.json")))
+    table = {}
+    enc = lambda s: [table.setdefault(w, len(table)) for w in s.split()]
+    refs = [enc(r["ref"]) for r in z["pairs"]]
+    hyps = [enc(r["hyp"]) for r in z["pairs"]]
+    got = harness.edit_counts(lib, refs, hyps)
+    assert got.tolist() == [r["word"] for r in z["pairs"]]
+    crefs = [[ord(c) for c in r["ref"].strip().replace(" ", "_")] for r in z["pairs"]]
+    chyps = [[ord(c) for c in r["hyp"].strip().replace(" ", "_")] for r in z["pairs"]]
+    got = harness.edit_counts(lib, crefs, chyps)
+    assert got.tolist() == [r["char"] for r in z["pairs"]]
+    assert harness.edit_counts(lib, [], []).shape == (0, 4)
+
+
+def test_edit_counts_column_tiles(lib):
+    # hypotheses wider than one 256-column tile: the right edge of a tile is the next one's left edge
+    rng = np.random.default_rng(7)
+    refs, hyps = [], []
+    for n, m in [(300, 257), (40, 600), (520, 256), (1, 513), (257, 1), (64, 300), (255, 255), (256, 258)]:
+        r = rng.integers(0, 6, n).tolist()
+        h = (r[: m // 2] + rng.integers(0, 6, m).tolist())[:m]
+        refs.append(r); hyps.append(h)
+    got = harness.edit_counts(lib, refs, hyps)
+    assert got.tolist() == [_edit_vec(r, h) for r, h in zip(refs, hyps)]
