@@ -247,22 +247,20 @@ def bench_loss(args, rank, world, dev):
     global_b = B * world
 
     def step(i):
+        # gradients are scaled by the global batch in-kernel; the 2-scalar all-reduce of the loss value runs on
+        # NCCL's stream and is waited for where the value is read (end of the timed region)
         nll, grad = ops.ctc_loss_fwd_bwd(lps[i % nsets], il_d, tg_d, tl_d, blank=1, zero_infinity=True, mean_denominator=global_b)
-        mean, _ = (nll / tl_d.clamp_min(1)).sum(), None
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(mean)
-        return mean, grad
+        return sdist.global_mean_loss_async(nll, tl_d)
 
     for i in range(args.warmup):
-        step(i)
+        step(i)()
     barrier(world)
     l0 = ops.LAUNCHES["loss"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step(i)
+    pending = [step(i) for i in range(args.steps)]
+    for wait in pending:
+        wait()
     e1.record()
     barrier(world)
     ms_total = dist_max(e0.elapsed_time(e1), world, dev)
@@ -462,6 +460,8 @@ def main():
     from silent_speech_decoder_b200 import dist as sdist
 
     rank, world, local = sdist.init_from_env()
+    if world > 1:
+        sdist.bind_host_thread_to_gpu(local)  # pinned e2e buffers on the GPU's own NUMA node (N=1 keeps all cores for cpu_baseline)
     run_native(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist

@@ -982,6 +982,7 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
       if (rc == SSD_ERR_UNSUPPORTED) only = nullptr, only_count = nullptr;
     }
   }
+  if (only && env_int("SSD_LOSS_FASTONLY", 0)) return SSD_OK;  // timing experiments only: flagged rows stay unrecomputed
   LossParams P;
   P.only = only; P.only_count = only_count;
   P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;

@@ -54,10 +54,25 @@ constexpr int F_W = SSD_F_W;      // block workers
 constexpr int F_THREADS = 32 * (4 + F_W);  // MF MB LF LB + workers
 constexpr int F_H = SSD_F_H;      // frames per worker pass (rows a worker buffers)
 static_assert((F_W == 4 || F_W == 6) && (F_H == 4 || F_H == 8), "supported worker shapes");
-constexpr int F_NP = 3;    // probability-row ring depth per main (blocks)
-constexpr int F_NRAW = 3;  // raw-row ring depth per main
+#ifndef SSD_F_NP
+#define SSD_F_NP 3
+#endif
+#ifndef SSD_F_NRAW
+#define SSD_F_NRAW 3
+#endif
+constexpr int F_NP = SSD_F_NP;      // probability-row ring depth per main (blocks)
+constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
 #ifndef SSD_F_FR
 #define SSD_F_FR 4
+#endif
+#ifndef SSD_X
+#define SSD_X 0  // timing experiments only (profiles/build_variant.sh): 1 no checkpoint stores, 2 no renormalisation, 4 no sweep steps, 8 no class sums, 16 no gradient stores, 32 no mass check
+#endif
+#ifndef SSD_F_PFD
+#define SSD_F_PFD 0  // L2 prefetch distance of the loaders, in blocks (0 = off: no gain measured, warm or cold)
+#endif
+#ifndef SSD_F_LDSLEEP
+#define SSD_F_LDSLEEP 2000u  // ns between a loader's polls of its ring's empty barrier; 0 = hardware-suspended try_wait
 #endif
 #ifndef SSD_F_PAIR
 #define SSD_F_PAIR 1  // frame loops: 1 = two steps per trip with alternating probability registers, 0 = one step per trip
@@ -592,16 +607,34 @@ __device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan
     mbar_arrive_expect_tx(&mv.bar[FB_RAW + slot], bytes);
     bulk_g2s(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot]);
   };
-  if (P.use_tma && lane == 0)
+  // The rows come from HBM the first time (~1.5 us per bulk copy, measured: with F_NRAW - 1 = 2 copies in flight the
+  // ring delivered one block per ~1470 cycles and the sweeps starved).  A bulk L2 prefetch F_PFD blocks ahead costs
+  // no shared memory and turns the ring's copies into L2 hits.
+  auto prefetch = [&](int bi) {  // lane 0
+    const int q = blk_of(bi);
+    const int n = min(F_K, pl.Tb - q * F_K);
+    bulk_prefetch_l2(base + (int64_t)q * F_K * P.st, (uint32_t)(n * V * 4));
+  };
+  if (P.use_tma && lane == 0) {
     for (int bi = 0; bi < pl.NB && bi < F_NRAW - 1; ++bi) issue_raw(bi);
+    if (SSD_F_PFD)
+      for (int bi = F_NRAW - 1; bi < pl.NB && bi < SSD_F_PFD; ++bi) prefetch(bi);
+  }
   int lpbad = 0;
   for (int bi = 0; bi < pl.NB; ++bi) {
     __syncwarp();  // every lane is done with raw slot (bi-1) before lane 0 re-arms it
-    if (P.use_tma && lane == 0 && bi + F_NRAW - 1 < pl.NB) issue_raw(bi + F_NRAW - 1);
+    if (P.use_tma && lane == 0) {
+      if (bi + F_NRAW - 1 < pl.NB) issue_raw(bi + F_NRAW - 1);
+      if (SSD_F_PFD && bi + SSD_F_PFD < pl.NB) prefetch(bi + SSD_F_PFD);
+    }
     const unsigned Q = qbase + (unsigned)bi;
     const int slot = (int)(Q % F_NP);
     fstamp(P, uiter, bi, 0);
-    mbar_wait_relaxed(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u, 2000u);  // I am blocks ahead: no hurry
+#if SSD_F_LDSLEEP
+    mbar_wait_relaxed(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u, SSD_F_LDSLEEP);  // I am blocks ahead: no hurry
+#else
+    mbar_wait(&mv.bar[FB_PEMPTY + slot], ((Q / F_NP) & 1u) ^ 1u);
+#endif
     fstamp(P, uiter, bi, 1);
     const int q = blk_of(bi);
     const int n = min(F_K, pl.Tb - q * F_K);
@@ -653,15 +686,18 @@ __device__ void fast_main(const FastParams& P, const MainView& mv, const FPlan& 
     fstamp(P, uiter, bi, 1);
     const float* pblk = mv.p(slot);
     const int n = min(F_K, pl.Tb - q * F_K);
-    for_frames<NC, DIR>(pblk, 0, n, lt, blank_off, [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr, mid); });
+    if (!(SSD_X & 4))
+      for_frames<NC, DIR>(pblk, 0, n, lt, blank_off, [&](int, const FProbs<NC>& pc, auto&& mid) { fstep<NC, DIR, false>(s, in, lt, pc, nullptr, mid); });
     __syncwarp();
     if (lane == 0) mbar_arrive(&mv.bar[FB_PEMPTY + slot]);
     fstamp(P, uiter, bi, 2);
-    ok &= renorm_exchange<NC, DIR>(s);
-    inflow_prime<NC, DIR>(s, in);  // the values shuffled before the renormalisation are in the old basis
+    if (!(SSD_X & 2)) {
+      ok &= renorm_exchange<NC, DIR>(s);
+      inflow_prime<NC, DIR>(s, in);  // the values shuffled before the renormalisation are in the old basis
+    }
     const int qn = DIR ? q - 1 : q + 1;  // the block this state starts
     if (qn >= 0 && qn < pl.NB) {
-      ckpt_store<NC>(ck + (size_t)qn * P.ckpt_rec_bytes, s, pl.L);
+      if (!(SSD_X & 1)) ckpt_store<NC>(ck + (size_t)qn * P.ckpt_rec_bytes, s, pl.L);
       __syncwarp();
       if (lane == 0) mbar_arrive(&blk_ready[qn]);
     }
@@ -922,9 +958,9 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
         for (int f = 0; f < FR; ++f) tot[f] = gbl[f];
 #pragma unroll 1
         for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
-          const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
-          const int ml = (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
           float acc[FR];
+          const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
+          const int ml = (SSD_X & 8) ? 0 : (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
 #pragma unroll
           for (int f = 0; f < FR; ++f) acc[f] = 0.f;
 #pragma unroll 2
@@ -940,13 +976,13 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
           for (int f = 0; f < FR; ++f) {
             tot[f] += acc[f];
             const float gv = acc[f] + (v == P.blank ? gb[f] : 0.f);
-            if (f < nf && v < V) st_stream(g_base + (int64_t)(t0 + f0 + r0 + f) * P.st + v, (pv[f] - gv) * scale);
+            if (!(SSD_X & 16) && f < nf && v < V) st_stream(g_base + (int64_t)(t0 + f0 + r0 + f) * P.st + v, (pv[f] - gv) * scale);
           }
         }
         // D3: the posteriors of a frame sum to one unless mass was lost to fp32 range somewhere
 #pragma unroll
         for (int f = 0; f < FR; ++f) {
-          const float t = warp_sum_fx(tot[f]);
+          const float t = (SSD_X & 32) ? 1.f : warp_sum_fx(tot[f]);
           if (f < nf && !(fabsf(t - 1.f) <= F_MASS_TOL)) mass_ok = false;
         }
       }
@@ -1051,13 +1087,13 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     pl.b = b; pl.Tb = sc->T; pl.S = S; pl.L = 2 * S + 1;
     pl.NB = (pl.Tb + F_K - 1) / F_K;
     if (!skip) {
+      for (int q = tid; q < pl.NB; q += F_THREADS) mbar_init(&blk_ready[q], 2);  // MF's and MB's checkpoint
       // class histogram -> start offsets; position of every label in class-sorted order (stable)
       for (int v = tid; v < P.V; v += F_THREADS) {
         int c = 0;
         for (int j = 0; j < S; ++j) c += (lab[j] == v) ? 1 : 0;
         cls[v + 1] = c;
       }
-      for (int q = tid; q < pl.NB; q += F_THREADS) mbar_init(&blk_ready[q], 2);  // MF's and MB's checkpoint
       __syncthreads();
       if (tid == 0) {
         cls[0] = 0;

@@ -133,6 +133,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 #endif
 }
+// Hint: pull `bytes` (multiple of 16) at `src_gmem` into L2 ahead of the bulk copy that will fetch them
+// (cp.async.bulk.prefetch.L2, SASS UBLKPF).  No shared memory, no completion to wait for.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+#ifdef SSD_EMU
+  (void)src_gmem;
+  (void)bytes;
+#else
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+#endif
+}
 // generic-proxy writes to smem that the async proxy will overwrite later must be ordered first
 __device__ __forceinline__ void fence_proxy_async() {
 #ifndef SSD_EMU
@@ -146,7 +156,11 @@ __device__ __forceinline__ void st_stream(float* p, float v) {
 #ifdef SSD_EMU
   *p = v;
 #else
+#if defined(SSD_ST_ASM) && SSD_ST_ASM
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
+  __stcs(p, v);  // st.global.cs without a compiler barrier: the surrounding shared-memory loads may move across it
+#endif
 #endif
 }
 __device__ __forceinline__ void st_stream4(float4* p, float4 v) {

@@ -37,6 +37,23 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_host_thread_to_gpu(local_rank: int) -> bool:
+    """Pin the calling thread to the CPUs nearest ``cuda:local_rank`` (NVML's affinity mask), so the pinned host
+    buffers a rank allocates afterwards are first-touched on that GPU's NUMA node.  With eight ranks copying
+    log-probs to eight GPUs at once the host side of the copy is what they share.  Best effort: False when NVML
+    or the affinity call is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        return True
+    except Exception:
+        return False
+
+
 def shard_by_cost(lengths: Sequence[int], world: int) -> List[List[int]]:
     """Deal utterances to ranks longest-first, round-robin (decode cost grows with T)."""
     order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
@@ -97,10 +114,33 @@ def sharded_decode(decode_ids: Callable[[torch.Tensor, torch.Tensor], List[List[
     return gather_ragged(rows, mine, int(lengths.numel()), group)
 
 
+def _loss_parts(nll: torch.Tensor, target_lengths: torch.Tensor) -> torch.Tensor:
+    # everything stays on the stream: no host-side scalar is copied in (that would synchronise the step)
+    s = (nll / target_lengths.to(nll.device).clamp_min(1)).sum(dtype=torch.float64)
+    return torch.stack([s, torch.full_like(s, float(nll.numel()))])
+
+
 def global_mean_loss(nll: torch.Tensor, target_lengths: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
     """'mean' reduction over the GLOBAL batch from local per-utterance nll. One all-reduce of 2 scalars."""
-    tl = target_lengths.to(nll.device).clamp_min(1).to(torch.float64)
-    part = torch.stack([(nll.double() / tl).sum(), torch.tensor(float(nll.numel()), dtype=torch.float64, device=nll.device)])
+    part = _loss_parts(nll, target_lengths)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
     return (part[0] / part[1]).to(nll.dtype), int(round(float(part[1])))
+
+
+def global_mean_loss_async(nll: torch.Tensor, target_lengths: torch.Tensor, group=None) -> Callable[[], torch.Tensor]:
+    """Same reduction, issued on the collective's own stream: returns a function that waits for it and gives the
+    mean.  The gradient never needs the reduced value (it is scaled by the global batch size in-kernel,
+    ``mean_denominator``), so a training step calls this right after the loss launch, carries on with the backward
+    pass of the encoder, and reads the number when it logs it."""
+    part = _loss_parts(nll, target_lengths)
+    work = None
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def result() -> torch.Tensor:
+        if work is not None:
+            work.wait()
+        return (part[0] / part[1]).to(nll.dtype)
+
+    return result

@@ -35,6 +35,8 @@ def _worker(rank, world, port, q):
     lo, hi = (0, 6) if rank == 0 else (6, 11)
     nll, _, _ = ol.torch_ctc(lp[lo:hi], ln[lo:hi], tg[lo:hi], tl[lo:hi], 1, True, torch.float64)
     mean, n = sdist.global_mean_loss(nll, tl[lo:hi])
+    later = sdist.global_mean_loss_async(nll, tl[lo:hi])  # same number through the overlapped form
+    assert float(later()) == float(mean)
     q.put((rank, rows, float(mean), n))
     dist.barrier()
     dist.destroy_process_group()
