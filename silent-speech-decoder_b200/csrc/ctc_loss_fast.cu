@@ -62,6 +62,17 @@ static_assert((F_W == 4 || F_W == 6) && (F_H == 4 || F_H == 8), "supported worke
 #endif
 constexpr int F_NP = SSD_F_NP;      // probability-row ring depth per main (blocks)
 constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
+#ifndef SSD_F_CU
+#define SSD_F_CU 1  // unroll of the log-prob -> probability conversion loop (2V/32 trips)
+#endif
+#ifndef SSD_F_CP
+#define SSD_F_CP 2  // class passes summed per trip of the range-sum loop (1 or 2)
+#endif
+#ifndef SSD_F_KU
+#define SSD_F_KU 2  // unroll of the class range-sum loop
+#endif
+#define SSD_PRAGMA_(x) _Pragma(#x)
+#define SSD_UNROLL(n) SSD_PRAGMA_(unroll n)
 #ifndef SSD_F_FR
 #define SSD_F_FR 4
 #endif
@@ -548,7 +559,7 @@ __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, co
                                                float* __restrict__ pblk) {
   const int lane = lane_id();
   float amax = 0.f;  // largest |log-prob| seen (a NaN passes here and poisons Z or a frame's mass instead)
-#pragma unroll 1
+  SSD_UNROLL(SSD_F_CU)
   for (int base = 0; base < 2 * V; base += 32) {
     int idx = base + lane;  // item = (frame quad, class): consecutive lanes, consecutive classes
     const bool live = idx < 2 * V;
@@ -956,27 +967,43 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
         float tot[FR];
 #pragma unroll
         for (int f = 0; f < FR; ++f) tot[f] = gbl[f];
+        constexpr int CP = SSD_F_CP;  // class passes (32 classes each) summed together: more independent loads per trip
 #pragma unroll 1
-        for (int ci = 0, v = lane; ci < ncls_it; ++ci, v += 32) {
-          float acc[FR];
-          const int ca = v < V ? cls[v] : 0, cb = v < V ? cls[v + 1] : 0;
-          const int ml = (SSD_X & 8) ? 0 : (mlen >> (8 * ci)) & 0xff;  // longest range among this pass's classes
+        for (int ci = 0; ci < ncls_it; ci += CP) {
+          float acc[CP][FR];
+          int ca[CP], cb[CP];
+          int ml = 0;
 #pragma unroll
-          for (int f = 0; f < FR; ++f) acc[f] = 0.f;
-#pragma unroll 2
-          for (int k = 0; k < ml; ++k) {
-            const int idx = ca + k < cb ? ca + k : F_SPAD + 32;  // out of range: a slot that always holds zero
+          for (int c = 0; c < CP; ++c) {
+            const int v = lane + 32 * (ci + c);
+            ca[c] = v < V ? cls[v] : 0;
+            cb[c] = v < V ? cls[v + 1] : 0;
+            ml = max(ml, ci + c < ncls_it ? (int)((mlen >> (8 * (ci + c))) & 0xff) : 0);  // longest range among these classes
 #pragma unroll
-            for (int f = 0; f < FR; ++f) acc[f] += gfp[f][idx];
+            for (int f = 0; f < FR; ++f) acc[c][f] = 0.f;
           }
-          float pv[FR];
+          if (SSD_X & 8) ml = 0;
+          SSD_UNROLL(SSD_F_KU)
+          for (int k = 0; k < ml; ++k) {
 #pragma unroll
-          for (int f = 0; f < FR; ++f) pv[f] = v < V ? pblk[v * F_KS + f0 + r0 + (f < nf ? f : 0)] : 0.f;
+            for (int c = 0; c < CP; ++c) {
+              const int idx = ca[c] + k < cb[c] ? ca[c] + k : F_SPAD + 32;  // out of range: a slot that always holds zero
 #pragma unroll
-          for (int f = 0; f < FR; ++f) {
-            tot[f] += acc[f];
-            const float gv = acc[f] + (v == P.blank ? gb[f] : 0.f);
-            if (!(SSD_X & 16) && f < nf && v < V) st_stream(g_base + (int64_t)(t0 + f0 + r0 + f) * P.st + v, (pv[f] - gv) * scale);
+              for (int f = 0; f < FR; ++f) acc[c][f] += gfp[f][idx];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            const int v = lane + 32 * (ci + c);
+            float pv[FR];
+#pragma unroll
+            for (int f = 0; f < FR; ++f) pv[f] = v < V ? pblk[v * F_KS + f0 + r0 + (f < nf ? f : 0)] : 0.f;
+#pragma unroll
+            for (int f = 0; f < FR; ++f) {
+              tot[f] += acc[c][f];
+              const float gv = acc[c][f] + (v == P.blank ? gb[f] : 0.f);
+              if (!(SSD_X & 16) && f < nf && v < V) st_stream(g_base + (int64_t)(t0 + f0 + r0 + f) * P.st + v, (pv[f] - gv) * scale);
+            }
           }
         }
         // D3: the posteriors of a frame sum to one unless mass was lost to fp32 range somewhere
