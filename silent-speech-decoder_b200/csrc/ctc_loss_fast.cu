@@ -62,6 +62,9 @@ static_assert((F_W == 4 || F_W == 6) && (F_H == 4 || F_H == 8), "supported worke
 #endif
 constexpr int F_NP = SSD_F_NP;      // probability-row ring depth per main (blocks)
 constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
+#ifndef SSD_F_EARLYA
+#define SSD_F_EARLYA 0  // 1: a worker loads the alpha checkpoint together with the beta one (held in registers through the beta pass)
+#endif
 #ifndef SSD_F_CU
 #define SSD_F_CU 1  // unroll of the log-prob -> probability conversion loop (2V/32 trips)
 #endif
@@ -162,6 +165,7 @@ struct FastParams {
   int RS;  // worker row stride in floats
   int use_tma;
   int rotate;  // 1: the second CTA of an SM mirrors its role map (tuning knob SSD_LOSS_NOROT)
+  int late_worker;  // 1: the sweeps' ring space hosts one more worker once both sweeps are done (SSD_LOSS_NOLATE)
   long long* tlog;  // SSD_LOSS_DBG & 8: [F_THREADS/32 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
 };
 constexpr int F_TLOG_N = 256, F_TLOG_S = 6;
@@ -181,7 +185,7 @@ struct FastSmem {  // byte offsets into dynamic shared memory, identical on host
 
 // mbarrier indices: per main F_NP full + F_NP empty + F_NRAW raw; then z_ready; then 2 raw barriers per worker
 constexpr int FB_PFULL = 0, FB_PEMPTY = F_NP, FB_RAW = 2 * F_NP, FB_PER_MAIN = 2 * F_NP + F_NRAW;
-constexpr int FB_Z = 2 * FB_PER_MAIN, FB_WRAW = FB_Z + 1, FB_TOTAL = FB_WRAW + 2 * F_W;
+constexpr int FB_Z = 2 * FB_PER_MAIN, FB_WRAW = FB_Z + 1, FB_TOTAL = FB_WRAW + 2 * (F_W + 1);  // + the late worker's pair
 
 // Probability blocks are stored class-major: p[v * F_KS + r] for the block's frame r (row V is the all-zero dummy
 // class of out-of-lattice cells).  A lane's label column is then ONE pointer for the whole block and a frame is
@@ -729,7 +733,7 @@ struct WorkerView {
 template <int NC>
 __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __restrict__ tab,
                             const int* __restrict__ cls, const WorkerView& wv, const unsigned char* ckpt_cta, uint64_t* blk_ready,
-                            uint64_t* z_ready, unsigned uiter, unsigned& nraw, FastScal* sc) {
+                            uint64_t* z_ready, unsigned uiter, unsigned& nraw, FastScal* sc, bool late) {
   const int lane = lane_id();
   const int V = P.V, RS = P.RS;
   const int blank_off = P.blank * F_KS * 4;  // bytes
@@ -764,7 +768,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes);
     bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
   };
-  bar_sync(1, 32 * (F_W + 2));  // released by the two mains shortly before the first block can be ready
+  if (!late) bar_sync(1, 32 * (F_W + 2));  // released by the two mains shortly before the first block can be ready
   int i = grab();
   if (i < nblk && P.use_tma && lane == 0) issue_raw(i, nraw);
   int nmine = 0;
@@ -806,6 +810,10 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
       {
         FStrip<NC> s;
         ckpt_load<NC>(ck_b + (size_t)q * P.ckpt_rec_bytes, s, pl.L);
+#if SSD_F_EARLYA
+        // the alpha checkpoint is not needed before the beta pass is over: its L2 latency hides behind that pass
+        if (f0 == 0) ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, sa, pl.L);
+#endif
         e_beta = s.e;
         if (f0 == 0) e_alpha = ld_cg(reinterpret_cast<const int*>(ck_a + (size_t)q * P.ckpt_rec_bytes + (size_t)NC * 32 * 4) + lane);
         if (z_known) {
@@ -842,7 +850,9 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
       FLabels<NC> la;
       load_labels<NC, 0>(la, tab);
       if (f0 == 0) {
+#if !SSD_F_EARLYA
         ckpt_load<NC>(ck_a + (size_t)q * P.ckpt_rec_bytes, sa, pl.L);
+#endif
         if (!z_known) {
           // Z = sum over the lattice of alpha_t * beta~_t at the block's first frame (unscaled pass)
           FStrip<NC> z = sa;
@@ -1019,6 +1029,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     i = i_next;
   }
   if (!mass_ok && lane == 0) atomicOr(&sc->uflag, 8);  // D3 (the sums are warp-uniform)
+  if (late) fence_proxy_async();  // my ordinary stores to the ring space precede the next utterance's bulk copies into it
 }
 
 // ------------------------------------------------------------------ kernel
@@ -1034,14 +1045,24 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
   int* tab = reinterpret_cast<int*>(smem + M.tab_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M.bar_off);
   uint64_t* blk_ready = reinterpret_cast<uint64_t*>(smem + M.blk_off);
-  FastScal* sc = reinterpret_cast<FastScal*>(smem + M.scal_off);
+  // The offsets here depend on launch parameters only, so ptxas keeps them in uniform registers -- and ptxas 12.9 has
+  // been caught (cuda-gdb + SASS: `MOV R, UR4 ; LDS [R+UR8+0x14]` at the workers' entry with UR4 long since holding
+  // V+1) re-materialising this kernel's copy of the scalar block's offset from a uniform register that the role code
+  // had reused: every access to *sc then went to a wrong, even misaligned, shared address, in builds that differed
+  // from a working one by a moved load.  The offset therefore takes a round trip through shared memory (a volatile
+  // load cannot be re-materialised from anything but memory); a shuffle is not enough, it is folded away.
+#ifndef SSD_EMU
+  __shared__ unsigned pin_scal;
+  if (tid == 0) pin_scal = (unsigned)M.scal_off;
+#endif
   uint64_t* z_ready = bars + FB_Z;
 
   if (tid == 0) {
     for (int i = 0; i < FB_TOTAL; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
-  // the dummy class (row V) of every probability block stays zero for the whole launch
+  // the dummy class (row V) of every probability block is zero; the workers' stay so for the whole launch, the
+  // sweeps' are restored per utterance (a late worker's rows overlay them)
   for (int i = tid; i < (2 * F_NP + F_W) * F_K; i += F_THREADS) {
     const int blk = i / F_K, r = i - blk * F_K;
     unsigned char* base = blk < 2 * F_NP ? smem + M.main_off + (size_t)(blk / F_NP) * M.main_bytes + (size_t)(blk % F_NP) * M.p_slot
@@ -1049,6 +1070,11 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     reinterpret_cast<float*>(base)[P.V * F_KS + r] = 0.f;
   }
   __syncthreads();
+#ifdef SSD_EMU
+  FastScal* sc = reinterpret_cast<FastScal*>(smem + M.scal_off);
+#else
+  FastScal* sc = reinterpret_cast<FastScal*>(smem + *reinterpret_cast<volatile unsigned*>(&pin_scal));
+#endif
 
   unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
   unsigned qbase = 0u, uiter = 0u, nraw = 0u;
@@ -1103,6 +1129,13 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     __syncthreads();
     if (sc->utt >= P.B) break;
     const int b = sc->b, S = sc->S;
+    if (P.late_worker && uiter > 0u) {  // the previous utterance's late worker had its rows over the sweeps' rings
+      for (int i = tid; i < 2 * F_NP * F_K; i += F_THREADS) {
+        const int blk = i / F_K, r = i - blk * F_K;
+        unsigned char* base = smem + M.main_off + (size_t)(blk / F_NP) * M.main_bytes + (size_t)(blk % F_NP) * M.p_slot;
+        reinterpret_cast<float*>(base)[P.V * F_KS + r] = 0.f;
+      }
+    }
     for (int j = tid; j < S; j += F_THREADS) {
       const int64_t y = P.targets[(int64_t)b * P.tgt_stride + j];
       if (y < 0 || y >= P.V) sc->skip = sc->uflag = 1;  // benign race: every writer stores 1
@@ -1142,6 +1175,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
         for (int64_t r = pl.Tb + warp; r < P.T; r += F_THREADS / 32)
           for (int v = lane; v < P.V; v += 32) st_stream(g0 + r * P.st + v, 0.f);
       }
+      int wslot = role >= 4 ? role - 4 : -1;  // worker buffer set: 0..F_W-1, F_W = the sweeps' ring space (late worker)
       if (role < 4) {
         const int h = role & 1;
         MainView mv;
@@ -1153,16 +1187,29 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
         else if (role == 1) fast_main<NC, 1>(P, mv, pl, tab, qbase, ckpt_cta, blk_ready, sc, uiter);
         else if (role == 2) fast_loader<0>(P, mv, pl, qbase, sc, uiter);
         else fast_loader<1>(P, mv, pl, qbase, sc, uiter);
-      } else {
-        const int w = role - 4;
-        unsigned char* wb = smem + M.worker_off + (size_t)w * M.worker_bytes;
+        // Both sweeps and both loaders are done well before the workers are (the workers' share is ~2/3 of an
+        // utterance's time): one of these four warps joins the workers for the rest of the utterance, with the
+        // sweeps' ring space -- idle from here on -- as its buffers.
+        if (P.late_worker && P.grad) {
+          bar_sync(2, 128);  // all four: nobody reads or fills the rings any more
+          if (role == 2) wslot = F_W;
+        }
+      }
+      if (wslot >= 0) {
+        const bool late = wslot == F_W;
+        unsigned char* wb = late ? smem + M.main_off : smem + M.worker_off + (size_t)wslot * M.worker_bytes;
         WorkerView wv;
         wv.rows = reinterpret_cast<float*>(wb);
         wv.pblk = reinterpret_cast<float*>(wb + M.wrow_bytes);
         wv.raw0 = reinterpret_cast<float*>(wb + M.wrow_bytes + M.p_slot);
         wv.raw_stride = (int)(M.raw_slot / 4);
-        wv.rawbar = bars + FB_WRAW + 2 * w;
-        fast_worker<NC>(P, pl, tab, cls, wv, ckpt_cta, blk_ready, z_ready, uiter, nraw, sc);
+        wv.rawbar = bars + FB_WRAW + 2 * wslot;
+        if (late) {
+          if (lane < F_K) wv.pblk[P.V * F_KS + lane] = 0.f;  // the dummy class of this block buffer
+          __syncwarp();
+          fence_proxy_async();  // bytes last written by ordinary stores are about to be written by bulk copies
+        }
+        fast_worker<NC>(P, pl, tab, cls, wv, ckpt_cta, blk_ready, z_ready, uiter, nraw, sc, late);  // the only call site
       }
       qbase += (unsigned)pl.NB;
       ++uiter;
@@ -1220,6 +1267,10 @@ static bool fast_plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, FastPl
   if (pl.smem > 113 * 1024) return false;
   const int64_t slots = (int64_t)fast_device_sms() * 2;
   pl.grid = (int)(B < slots ? B : slots);
+  {  // test knob: fewer CTAs than utterances, so that a CTA walks through several of them
+    const int cap = fast_env_int("SSD_LOSS_GRID", 0);
+    if (cap > 0 && cap < pl.grid) pl.grid = cap;
+  }
   pl.ckpt_rec_bytes = (size_t)pl.NC * 32 * 4 + 128;
   pl.ckpt_cta_bytes = (size_t)2 * pl.nb_max * pl.ckpt_rec_bytes;
   pl.ws_bytes = 256 + 4096 + (((size_t)B * 4 + 255) & ~(size_t)255) + (size_t)pl.grid * pl.ckpt_cta_bytes + (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8;
@@ -1272,6 +1323,10 @@ int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t s
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
   if (fast_env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;
   P.rotate = fast_env_int("SSD_LOSS_NOROT", 0) ? 0 : 1;
+  {
+    const FastSmem m = fast_smem_layout((int)V, pl.RS, (int)S_max + 4, pl.nb_max);
+    P.late_worker = (m.worker_bytes <= 2 * m.main_bytes && !fast_env_int("SSD_LOSS_NOLATE", 0)) ? 1 : 0;
+  }
   P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8) : nullptr;
   *flags = P.flags;
   *nflag = P.counter + 1;

@@ -201,3 +201,22 @@ def test_edit_counts_column_tiles(lib):
         refs.append(r); hyps.append(h)
     got = harness.edit_counts(lib, refs, hyps)
     assert got.tolist() == [_edit_vec(r, h) for r, h in zip(refs, hyps)]
+
+
+def test_loss_fast_path_several_utterances_per_cta(lib, monkeypatch):
+    # 2 CTAs for 7 ragged utterances: scalars, label tables, rings and the late worker's overlay of the sweeps'
+    # ring space are rebuilt per utterance
+    monkeypatch.setenv("SSD_LOSS_GRID", "2")
+    lp = synth.flat(7, 90, 31).numpy()
+    tg, tl = synth.targets(7, 20, 32)
+    il = synth.ragged_lengths(7, 90, 33).numpy()
+    il[3] = 90
+    want_nll, _, want_g = ol.torch_ctc(torch.from_numpy(lp), torch.from_numpy(il), tg, tl, 1, True, torch.float64)
+    nll, g, flags = harness.loss(lib, lp, il, tg.numpy(), tl.numpy(), 1, mean_den=7, with_fallbacks="flags")
+    assert not flags.any()
+    np.testing.assert_allclose(nll, want_nll.numpy(), rtol=2e-6)
+    assert np.abs(g - want_g.numpy()).max() <= 1e-5 * np.abs(want_g.numpy()).max()
+    monkeypatch.setenv("SSD_LOSS_NOLATE", "1")
+    nll2, g2, _ = harness.loss(lib, lp, il, tg.numpy(), tl.numpy(), 1, mean_den=7, with_fallbacks="flags")
+    np.testing.assert_allclose(nll2, nll, rtol=1e-6)
+    assert np.abs(g2 - g).max() <= 2e-6 * np.abs(g).max()

@@ -183,3 +183,25 @@ def test_full_size_cfg2_properties():
     # determinism
     nll2, grad2 = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1)
     assert torch.equal(nll, nll2) and torch.equal(grad, grad2)
+
+
+@pytest.mark.timeout(180)
+def test_more_utterances_than_ctas(monkeypatch):
+    """700 ragged utterances on at most 296 CTAs: every CTA walks through several utterances, its late worker
+    (one of the sweep warps, once the sweeps are done) re-using the sweeps' ring space each time.  Checked against
+    the exact fp64 kernel of the same library, and against itself without the late worker."""
+    B, T, S = 700, 160, 40
+    lp = synth.flat(B, T, 71).cuda()
+    tg, tl = synth.targets(B, S, 72)
+    il = synth.ragged_lengths(B, T, 73)
+    nll, g = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
+    assert ops.loss_fallback_count(B, T, 48, S) == 0
+    monkeypatch.setenv("SSD_LOSS_EXACT", "1")
+    nll_x, g_x = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
+    monkeypatch.delenv("SSD_LOSS_EXACT")
+    assert ((nll - nll_x).abs() / nll_x.abs()).max().item() < 2e-6
+    assert (g - g_x).abs().max().item() <= 1e-5 * g_x.abs().max().item()
+    monkeypatch.setenv("SSD_LOSS_NOLATE", "1")
+    nll_b, g_b = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
+    monkeypatch.delenv("SSD_LOSS_NOLATE")
+    assert torch.equal(nll_b, nll) and torch.equal(g_b, g)  # who computes a block does not change a single bit
