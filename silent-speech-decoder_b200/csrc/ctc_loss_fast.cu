@@ -790,7 +790,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     ++nraw;
     convert_block(raw, lp_base + (int64_t)t0 * P.st, P.st, n, V, pblk);
     fstamp(P, uiter, nmine, 1);
-    mbar_wait_relaxed(&blk_ready[q], 0u);  // both checkpoints of the block are published
+    mbar_wait_relaxed(&blk_ready[q], uiter & 1u);  // both checkpoints of the block are published
     fstamp(P, uiter, nmine, 2);
     fstamp(P, uiter, nmine, 5, q);
     __syncwarp();
@@ -1061,6 +1061,11 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     for (int i = 0; i < FB_TOTAL; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
+  // One object per block, initialised ONCE per launch (MF's and MB's checkpoint = 2 arrivals).  Every utterance
+  // moves every object on by exactly one phase -- the blocks it does not have get their two arrivals right away --
+  // so the phase to wait for is the utterance count's parity.  (Re-initialising the objects per utterance left
+  // workers asleep on the B200 when a CTA alone on its SM ran through three or more short utterances.)
+  for (int q = tid; q < P.nb_max; q += F_THREADS) mbar_init(&blk_ready[q], 2);
   // the dummy class (row V) of every probability block is zero; the workers' stay so for the whole launch, the
   // sweeps' are restored per utterance (a late worker's rows overlay them)
   for (int i = tid; i < (2 * F_NP + F_W) * F_K; i += F_THREADS) {
@@ -1147,7 +1152,10 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     pl.b = b; pl.Tb = sc->T; pl.S = S; pl.L = 2 * S + 1;
     pl.NB = (pl.Tb + F_K - 1) / F_K;
     if (!skip) {
-      for (int q = tid; q < pl.NB; q += F_THREADS) mbar_init(&blk_ready[q], 2);  // MF's and MB's checkpoint
+      for (int q = pl.NB + tid; q < P.nb_max; q += F_THREADS) {  // blocks this utterance does not have
+        mbar_arrive(&blk_ready[q]);
+        mbar_arrive(&blk_ready[q]);
+      }
       // class histogram -> start offsets; position of every label in class-sorted order (stable)
       for (int v = tid; v < P.V; v += F_THREADS) {
         int c = 0;

@@ -189,7 +189,7 @@ def test_full_size_cfg2_properties():
 def test_more_utterances_than_ctas(monkeypatch):
     """700 ragged utterances on at most 296 CTAs: every CTA walks through several utterances, its late worker
     (one of the sweep warps, once the sweeps are done) re-using the sweeps' ring space each time.  Checked against
-    the exact fp64 kernel of the same library, and against itself without the late worker."""
+    the exact fp64 kernel of the same library, and against itself on fewer CTAs and without the late worker."""
     B, T, S = 700, 160, 40
     lp = synth.flat(B, T, 71).cuda()
     tg, tl = synth.targets(B, S, 72)
@@ -201,7 +201,14 @@ def test_more_utterances_than_ctas(monkeypatch):
     monkeypatch.delenv("SSD_LOSS_EXACT")
     assert ((nll - nll_x).abs() / nll_x.abs()).max().item() < 2e-6
     assert (g - g_x).abs().max().item() <= 1e-5 * g_x.abs().max().item()
-    monkeypatch.setenv("SSD_LOSS_NOLATE", "1")
-    nll_b, g_b = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
-    monkeypatch.delenv("SSD_LOSS_NOLATE")
-    assert torch.equal(nll_b, nll) and torch.equal(g_b, g)  # who computes a block does not change a single bit
+    # fewer CTAs (some alone on their SM, up to 19 utterances each; one CTA for a short prefix) and no late worker:
+    # who computes a block, and when, does not change a single bit.  The capped grids are the regression test for
+    # the per-utterance mbarrier re-initialisation that used to leave workers asleep in exactly this regime.
+    for env, n in (({"SSD_LOSS_GRID": "148"}, B), ({"SSD_LOSS_GRID": "37"}, B), ({"SSD_LOSS_NOLATE": "1"}, B),
+                   ({"SSD_LOSS_GRID": "1"}, 9), ({"SSD_LOSS_GRID": "1", "SSD_LOSS_NOLATE": "1"}, 9)):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        nll_b, g_b = ops.ctc_loss_fwd_bwd(lp[:n], il[:n], tg[:n], tl[:n], blank=1, mean_denominator=B)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert torch.equal(nll_b, nll[:n]) and torch.equal(g_b, g[:n]), env
