@@ -214,7 +214,7 @@ def run_reference(args, rank):
         val, ms, cores = cpu_loss_reference(args.steps, args.warmup)
         line = {"metric": "ctc_loss_fwd_bwd_frames_per_sec", "value": val, "unit": "frames/s", "ms_per_step": ms,
                 "sample": "full config 2 batch per step", "cores": cores, "kind": "reference",
-                "workload": "cfg2: CTC loss fwd+bwd B=256 T=1000 V=48 S~U[50,200]"}
+                "workload": "cfg2: CTC loss fwd+bwd B=256 T=1000 V=48 S~U[50,200] per GPU (configs[1])"}
     else:
         val, cores, n, one = cpu_beam_reference(256, args.beam_input)
         line = {"metric": "ctc_beam50_decode_utterances_per_sec", "value": val, "unit": "utterances/s", "ms_per_step": 1e3 * n / val,
