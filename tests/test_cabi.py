@@ -41,6 +41,11 @@ def test_argument_validation_needs_no_device(lib):
         lib.check(_native.SSD_ERR_BAD_ARG)
     with pytest.raises(_native.NativeError):
         lib.check(_native.SSD_ERR_CUDA)
+    assert lib.ssd_edit_counts(None, None, None, None, -1, 0, 0, None, None) == _native.SSD_ERR_BAD_ARG
+    assert lib.ssd_edit_counts(None, None, None, None, 4, 10, 10, None, None) == _native.SSD_ERR_BAD_ARG  # NULL offsets
+    assert lib.ssd_edit_counts(None, None, None, None, 0, 9000, 1, None, None) == _native.SSD_ERR_UNSUPPORTED
+    assert b"SSD_MAX_EDIT_LEN" in lib.ssd_last_error()
+    assert lib.ssd_edit_counts(None, None, None, None, 0, 0, 0, None, None) == _native.SSD_OK  # nothing to do
     assert lib.ssd_ctc_loss_workspace_bytes(256, 1000, 48, 200) > 256
     assert lib.ssd_ctc_beam_workspace_bytes(16, 500, 48, 50) > 256
 
