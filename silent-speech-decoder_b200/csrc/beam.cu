@@ -709,17 +709,16 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
           if (c == space_lbl) { hl = ho; ho = 0ull; }
           else ho = hmix(ho, (uint32_t)c);
         }
-        sel_hk[r] = hmix(hl ^ hmix(ho, 0x5bu), 0xa7u);
-        sel_lc[r] = lc;
+        // one 64-bit key for (last word, open word, last char): the duplicate scan below then compares one value
+        sel_hk[r] = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);
       }
       for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
       cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
         const uint64_t hk = sel_hk[r];
-        const int lc = sel_lc[r];
         int keep = 1;
         for (int q = 0; q < r; ++q)
-          if (sel_hk[q] == hk && sel_lc[q] == lc) { keep = 0; break; }
+          if (sel_hk[q] == hk) { keep = 0; break; }
         const uint32_t d = cdesc[sel[r]];
         const int c = (int)(d & 0xFFu);
         if (keep && (c == 0 || c == 0xFE)) {
