@@ -212,3 +212,16 @@ def test_more_utterances_than_ctas(monkeypatch):
         for k in env:
             monkeypatch.delenv(k)
         assert torch.equal(nll_b, nll[:n]) and torch.equal(g_b, g[:n]), env
+
+
+@pytest.mark.timeout(300)
+def test_random_shapes_against_exact_kernel():
+    """profiles/fuzz_loss.py: random (B, T, S, input kind, grid cap, late worker) against the exact fp64 kernel of the same
+    library, each case under a watchdog; exits 2 on a tolerance miss, 3 on a hang."""
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "profiles", "fuzz_loss.py"), "40", "5"], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all 40 cases ok" in r.stdout
