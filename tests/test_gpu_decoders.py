@@ -147,3 +147,15 @@ def test_beam_full_size_properties():
     g = ctc.build_decoder("greedy", V)(lp, ln)
     agree = sum(x == " ".join(y.split()) for x, y in zip(a, g))
     assert agree >= 0.95 * len(a)
+
+
+@pytest.mark.timeout(300)
+def test_beam_random_configurations():
+    """profiles/fuzz_beam.py: random (B, T, width, prune, blank bias, input kind, ragged lengths incl. 0) against the CPU
+    restatement: transcripts identical, scores within 1e-4."""
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "profiles", "fuzz_beam.py"), "30", "7"], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
