@@ -165,7 +165,7 @@ struct FastParams {
   int RS;  // worker row stride in floats
   int use_tma;
   int rotate;  // 1: the second CTA of an SM mirrors its role map (tuning knob SSD_LOSS_NOROT)
-  int late_worker;  // 1: the sweeps' ring space hosts one more worker once both sweeps are done (SSD_LOSS_NOLATE)
+  int late_worker;  // how many more workers (0..2) the sweeps' ring space hosts once both sweeps are done (SSD_LOSS_NOLATE)
   long long* tlog;  // SSD_LOSS_DBG & 8: [F_THREADS/32 warps][F_TLOG_N events][F_TLOG_S stamps] clock64 of CTA 0's first utterance
 };
 constexpr int F_TLOG_N = 256, F_TLOG_S = 6;
@@ -185,7 +185,7 @@ struct FastSmem {  // byte offsets into dynamic shared memory, identical on host
 
 // mbarrier indices: per main F_NP full + F_NP empty + F_NRAW raw; then z_ready; then 2 raw barriers per worker
 constexpr int FB_PFULL = 0, FB_PEMPTY = F_NP, FB_RAW = 2 * F_NP, FB_PER_MAIN = 2 * F_NP + F_NRAW;
-constexpr int FB_Z = 2 * FB_PER_MAIN, FB_WRAW = FB_Z + 1, FB_TOTAL = FB_WRAW + 2 * (F_W + 1);  // + the late worker's pair
+constexpr int FB_Z = 2 * FB_PER_MAIN, FB_WRAW = FB_Z + 1, FB_TOTAL = FB_WRAW + 2 * (F_W + 2);  // + the late workers' pairs
 
 // Probability blocks are stored class-major: p[v * F_KS + r] for the block's frame r (row V is the all-zero dummy
 // class of out-of-lattice cells).  A lane's label column is then ONE pointer for the whole block and a frame is
@@ -1201,11 +1201,12 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
         if (P.late_worker && P.grad) {
           bar_sync(2, 128);  // all four: nobody reads or fills the rings any more
           if (role == 2) wslot = F_W;
+          if (role == 3 && P.late_worker > 1) wslot = F_W + 1;  // room for a second one (smaller row buffers, deeper rings)
         }
       }
       if (wslot >= 0) {
-        const bool late = wslot == F_W;
-        unsigned char* wb = late ? smem + M.main_off : smem + M.worker_off + (size_t)wslot * M.worker_bytes;
+        const bool late = wslot >= F_W;
+        unsigned char* wb = late ? smem + M.main_off + (size_t)(wslot - F_W) * M.worker_bytes : smem + M.worker_off + (size_t)wslot * M.worker_bytes;
         WorkerView wv;
         wv.rows = reinterpret_cast<float*>(wb);
         wv.pblk = reinterpret_cast<float*>(wb + M.wrow_bytes);
@@ -1333,7 +1334,8 @@ int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t s
   P.rotate = fast_env_int("SSD_LOSS_NOROT", 0) ? 0 : 1;
   {
     const FastSmem m = fast_smem_layout((int)V, pl.RS, (int)S_max + 4, pl.nb_max);
-    P.late_worker = (m.worker_bytes <= 2 * m.main_bytes && !fast_env_int("SSD_LOSS_NOLATE", 0)) ? 1 : 0;
+    P.late_worker = fast_env_int("SSD_LOSS_NOLATE", 0) ? 0 : (int)(2 * m.main_bytes / m.worker_bytes);
+    if (P.late_worker > 2) P.late_worker = 2;
   }
   P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8) : nullptr;
   *flags = P.flags;
