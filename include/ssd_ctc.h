@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SSD_ABI_VERSION 1
+#define SSD_ABI_VERSION 2
 
 enum {
   SSD_OK = 0,
@@ -51,6 +51,7 @@ enum {
 #define SSD_MAX_VOCAB 128      /* V */
 #define SSD_MAX_TARGET 511     /* S: extended length 2S+1 <= 1023 lanes of the alpha/beta recursion */
 #define SSD_MAX_BEAM 512       /* beam_width */
+#define SSD_MAX_BEAM_SETTINGS 8 /* decoder settings served by one ssd_ctc_beam_grid launch */
 #define SSD_MAX_EDIT_LEN 8191  /* tokens per sequence in ssd_edit_counts */
 
 int ssd_abi_version(void);
@@ -90,6 +91,28 @@ int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
                  int32_t* out_lengths, double* out_scores, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Decoder grid (scope row f-3): the reference sweeps its decoder over (beam_width, beam_prune_logp,
+ * blank_bias) points -- src/experiments/config_builder.py:68-93 -- by re-running the whole evaluation
+ * once per point (orchestrate.py:129-153,235-249).  Here ONE launch serves up to SSD_MAX_BEAM_SETTINGS
+ * points over the same resident batch: a work item is (setting, utterance).  Results are those of
+ * n_settings separate ssd_ctc_beam calls, bit for bit.
+ *   settings     HOST array [n_settings]
+ *   out_tokens   [n_settings, B, T] int32      out_lengths [n_settings, B] int32
+ *   out_scores   [n_settings, B] fp64 or NULL
+ *   workspace    ssd_ctc_beam_workspace_bytes(B * n_settings, T, V, widest beam_width) bytes
+ */
+typedef struct ssd_beam_setting {
+  int32_t beam_width;
+  float beam_prune_logp;
+  float blank_bias;
+  float token_min_logp;
+} ssd_beam_setting;
+int ssd_ctc_beam_grid(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                      const int64_t* lengths, const int32_t* order, int blank, int pad, int space,
+                      const ssd_beam_setting* settings, int n_settings, int32_t* out_tokens, int32_t* out_lengths,
+                      double* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * CTC loss, forward and backward in one launch (torch.nn.CTCLoss semantics, reduction 'none'
  * for the returned values; the gradient can be pre-scaled for reduction 'mean').
  *   targets        [B, >=S_max] int64 padded label matrix with row stride tgt_stride (elements)
@@ -118,6 +141,35 @@ int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
                  const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
                  int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The same loss from LOGITS (scope row f-2).  The reference's head ends in log_softmax
+ * (src/models/heads.py:36-37) and its loss starts from those log-probs (src/models/losses.py:53-56);
+ * this entry consumes the head's pre-softmax output and returns the gradient with respect to it:
+ *   grad[b,t,:] = scale_b * (softmax(logits[b,t,:]) - posterior)   (the same numbers ssd_ctc_loss writes:
+ *   rows of exp(lp) - posterior sum to zero, so log_softmax's backward is the identity on them).
+ * A pre-pass reads the logits once and writes one fp32 log-sum-exp per frame into the workspace; the
+ * (B,T,V) log-prob tensor and its gradient never exist.  Arguments as ssd_ctc_loss; the workspace is
+ * ssd_ctc_loss_from_logits_workspace_bytes(...) bytes, laid out [ssd_ctc_loss workspace | lse], so
+ * ssd_ctc_loss_fallback_counter_offset applies unchanged.
+ */
+size_t ssd_ctc_loss_from_logits_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
+int ssd_ctc_loss_from_logits(const float* logits, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                             const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
+                             const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
+                             int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Per-frame log-sum-exp of a (B,T,V) fp32 tensor: lse[b*lse_stride + t] = log sum_v exp(x[b,t,v]).
+ * The pre-pass of ssd_ctc_loss_from_logits, exported for callers that keep the values. */
+int ssd_row_logsumexp(const float* x, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t, float* lse,
+                      int64_t lse_stride, void* stream);
+
+/* x[i] *= *g / expected for i < n -- unless *g == expected, in which case nothing but *g is read.
+ * autograd's backward of the fused loss: the gradient was written with the scalar the caller expects
+ * upstream (lambda_ctc of src/models/losses.py:104); the device-side test replaces a host
+ * synchronisation, and in the common case the whole read+write pass over the gradient. */
+int ssd_scale_if(float* x, int64_t n, const float* g, float expected, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Levenshtein alignment counts of N (reference, hypothesis) token sequences: the arithmetic of

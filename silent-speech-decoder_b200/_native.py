@@ -10,7 +10,7 @@ import ctypes as C
 from pathlib import Path
 from typing import Optional
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LIB_PATH = Path(__file__).resolve().parent / "libssd_ctc.so"
 
 SSD_OK, SSD_ERR_BAD_ARG, SSD_ERR_UNSUPPORTED, SSD_ERR_WORKSPACE, SSD_ERR_CUDA = range(5)
@@ -23,11 +23,22 @@ SIGNATURES = {
     "ssd_ctc_greedy": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I32, _F32, _P, _P, _P]),
     "ssd_ctc_beam_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "ssd_ctc_beam": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _F32, _I32, _F32, _F32, _P, _P, _P, _P, _SZ, _P]),
+    "ssd_ctc_beam_grid": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "ssd_ctc_loss_from_logits_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
+    "ssd_ctc_loss_from_logits": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "ssd_row_logsumexp": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
+    "ssd_scale_if": (C.c_int, [_P, _I64, _P, _F32, _P]),
     "ssd_ctc_loss_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_ctc_loss_fallback_counter_offset": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_edit_counts": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "ssd_ctc_loss": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
 }
+
+
+class BeamSetting(C.Structure):
+    """``ssd_beam_setting`` of include/ssd_ctc.h."""
+
+    _fields_ = [("beam_width", C.c_int32), ("beam_prune_logp", C.c_float), ("blank_bias", C.c_float), ("token_min_logp", C.c_float)]
 
 
 class NativeError(RuntimeError):

@@ -20,7 +20,7 @@ CSRC = PKG_DIR / "csrc"
 INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libssd_ctc.so"
 OBJ_DIR = PKG_DIR / "build"
-SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "capi.cu"]
+SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "aux.cu", "capi.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

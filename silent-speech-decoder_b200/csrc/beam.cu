@@ -16,10 +16,20 @@
 // Per frame (4 consumer warps; warp 4 conditions the next frame's row concurrently):
 //   1  tot = logaddexp(sb, snb); locate parent prefix through the shared-memory hash table
 //   2  rank prefixes by tot; blank / repeat / parent-extension scores of every live prefix
-//   3  proposals P+c.  With prefixes ranked by tot and candidate labels by log-prob, proposal
-//      (i,j) is dominated by (i+1)*j others, so only j <= W/(i+1) can reach the top W: about
-//      W(ln W + 1.6) proposals instead of W*46.  Proposals whose text is already a live prefix are
-//      folded into that prefix's snb (step 2) and dropped here.
+//   3  proposals P+c.  With prefixes ranked by tot (rank i = 0,1,..) and candidate labels by log-prob (column
+//      j = 0,1,..), row i keeps its first J_i = floor(W/(i+1)) + 1 columns: about W(ln W + 1.6) proposals instead
+//      of W*46.  Proposals whose text is already a live prefix are folded into that prefix's snb (step 2) and
+//      dropped here.
+//      Why nothing that could reach the top W is dropped.  Take (i,j) with j >= J_i.  Every (i',j') with
+//      i' <= i, j' <= j other than (i,j) itself has base tot_{i'} >= tot_i and log-prob r_{j'} >= r_j, so it
+//      scores at least as much -- EXCEPT the one column per row i' whose label equals that prefix's last
+//      character: that proposal is scored from sb_{i'} (not tot_{i'}), or, for an absorbed space, is not a
+//      proposal at all.  A folded proposal does not weaken the count: it lives on as the char-ended entry of
+//      its child, whose score lse(rep, ext) >= ext is at least the proposal's, and distinct (i',j') fold into
+//      distinct children.  So at least i*j + (j-1) distinct entries score >= (i,j): rows above contribute
+//      j+1 columns minus at most one each, row i contributes j columns minus at most one.  With
+//      j >= J_i = ceil((W+1)/(i+1)) that is >= (i+1)*j - 1 >= W entries ahead of (i,j): it cannot be among the
+//      top W (exact ties aside, which the parity inputs avoid).
 //   4  block max, relative prune, exact top-W by rank counting (ties: lower candidate index)
 //   5  history prune: best entry per (last closed word, open word, last char)
 //   6  compact survivors into the next prefix table, append back-pointer nodes, rebuild hash table
@@ -47,7 +57,12 @@ struct BeamParams {
   const int64_t* lengths;
   const int32_t* order;
   int blank, pad, space;
-  float bias, prune, tmin;
+  // decoder settings served by this launch (scope row f-3: the reference re-runs its whole evaluation once per
+  // (width, prune, blank bias) point of config_builder.py:68-93; here a work item is (setting, utterance) and all
+  // settings read the same resident batch).  W is the CAPACITY = the widest setting: it sizes shared memory.
+  int n_set;
+  int set_w[SSD_MAX_BEAM_SETTINGS];
+  float set_bias[SSD_MAX_BEAM_SETTINGS], set_prune[SSD_MAX_BEAM_SETTINGS], set_tmin[SSD_MAX_BEAM_SETTINGS];
   int W;
   int32_t* out_tok;
   int32_t* out_len;
@@ -192,8 +207,8 @@ struct Scal {
 // ------------------------------------------------------------------ producer: condition one frame
 // All 32 lanes; labels k = lane, lane+32, ...  Mirrors ctc.py:76-87 and decode_beams' fp32
 // log-softmax + clip, then builds the candidate set {k: r_k >= tmin} | {argmax}.
-__device__ void condition_frame(const float* __restrict__ row, const BeamParams& P, const int* __restrict__ lab2voc, FrameRec fr,
-                                int* nc1_out) {
+__device__ void condition_frame(const float* __restrict__ row, const BeamParams& P, float bias, float tmin,
+                                const int* __restrict__ lab2voc, FrameRec fr, int* nc1_out) {
   const int lane = lane_id();
   constexpr int PER = SSD_MAX_VOCAB / 32;
   float x[PER];
@@ -205,7 +220,7 @@ __device__ void condition_frame(const float* __restrict__ row, const BeamParams&
     if (k < P.VL) {
       if (k == 0) {
         v = row[P.blank];
-        if (P.bias != 0.f) v = v + P.bias;
+        if (bias != 0.f) v = v + bias;
         if (P.pad >= 0 && P.pad != P.blank) v = logaddexp_f32(v, row[P.pad]);
       } else {
         v = row[lab2voc[k]];
@@ -253,7 +268,7 @@ __device__ void condition_frame(const float* __restrict__ row, const BeamParams&
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int k = lane + 32 * i;
-    if (k < P.VL) fr.rl[k] = (x[i] >= P.tmin || k == best_k) ? x[i] : -INFINITY;
+    if (k < P.VL) fr.rl[k] = (x[i] >= tmin || k == best_k) ? x[i] : -INFINITY;
   }
   __syncwarp();
   // order non-blank candidates by (log-prob desc, label asc) through rank counting
@@ -304,21 +319,22 @@ __device__ __forceinline__ int table_find(const unsigned long long* keys, const 
 __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
-  const int W = P.W, VL = P.VL, TS = P.TS, NCAND = P.NCAND;
+  const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
 
   Prefix gen[2];
-  carve_prefix(sp, gen[0], W);
-  carve_prefix(sp, gen[1], W);
-  double* tot = (double*)carve(sp, 8 * W);
-  double* newb = (double*)carve(sp, 8 * W);
-  double* newnb = (double*)carve(sp, 8 * W);
-  double* ext_in = (double*)carve(sp, 8 * W);
-  int* par = (int*)carve(sp, 4 * W);
-  int* rnk = (int*)carve(sp, 4 * W);
-  int* rank2p = (int*)carve(sp, 4 * W);
-  int* rowoff = (int*)carve(sp, 4 * W);
-  int* keepf = (int*)carve(sp, 4 * W);
-  int* oslot = (int*)carve(sp, 4 * W);
+  const int WC = P.W;  // capacity: every table below is sized for the widest setting of the launch
+  carve_prefix(sp, gen[0], WC);
+  carve_prefix(sp, gen[1], WC);
+  double* tot = (double*)carve(sp, 8 * WC);
+  double* newb = (double*)carve(sp, 8 * WC);
+  double* newnb = (double*)carve(sp, 8 * WC);
+  double* ext_in = (double*)carve(sp, 8 * WC);
+  int* par = (int*)carve(sp, 4 * WC);
+  int* rnk = (int*)carve(sp, 4 * WC);
+  int* rank2p = (int*)carve(sp, 4 * WC);
+  int* rowoff = (int*)carve(sp, 4 * WC);
+  int* keepf = (int*)carve(sp, 4 * WC);
+  int* oslot = (int*)carve(sp, 4 * WC);
   unsigned long long* tkeys = (unsigned long long*)carve(sp, 8 * TS);
   int* tvals = (int*)carve(sp, 4 * TS);
   double* cscore = (double*)carve(sp, 8 * NCAND);
@@ -328,13 +344,13 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
   int* abkt = (int*)carve(sp, 4 * NCAND);
   int* blist = (int*)carve(sp, 4 * NCAND);
   int* hist = (int*)carve(sp, 4 * 256);
-  double* bscore = (double*)carve(sp, 8 * (W + 1));
-  int* bidx = (int*)carve(sp, 4 * (W + 1));
-  int* sel = (int*)carve(sp, 4 * (W + 1));
-  int* sel_keep = (int*)carve(sp, 4 * (W + 1));
-  int* sel_slot = (int*)carve(sp, 4 * (W + 1));
-  uint64_t* sel_hk = (uint64_t*)carve(sp, 8 * (W + 1));
-  int* sel_lc = (int*)carve(sp, 4 * (W + 1));
+  double* bscore = (double*)carve(sp, 8 * (WC + 1));
+  int* bidx = (int*)carve(sp, 4 * (WC + 1));
+  int* sel = (int*)carve(sp, 4 * (WC + 1));
+  int* sel_keep = (int*)carve(sp, 4 * (WC + 1));
+  int* sel_slot = (int*)carve(sp, 4 * (WC + 1));
+  uint64_t* sel_hk = (uint64_t*)carve(sp, 8 * (WC + 1));
+  int* sel_lc = (int*)carve(sp, 4 * (WC + 1));
   FrameRec fr[2];
   for (int i = 0; i < 2; ++i) {
     fr[i].rl = (float*)carve(sp, 4 * VL);
@@ -375,8 +391,13 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
     if (tid == 0) sc->utt = (int)atomicAdd(P.counter, 1u);
     __syncthreads();
     const int u = sc->utt;
-    if (u >= P.B) break;
-    const int b = P.order ? P.order[u] : u;
+    if (u >= P.B * P.n_set) break;
+    // work item = (setting, utterance); settings come widest first, utterances longest first within a setting
+    const int si = u / P.B, ub = u - si * P.B;
+    const int W = P.set_w[si];
+    const float s_bias = P.set_bias[si], s_prune = P.set_prune[si], s_tmin = P.set_tmin[si];
+    const int b = P.order ? P.order[ub] : ub;
+    const int64_t ob = (int64_t)si * P.B + b;  // output row
     int64_t len64 = P.lengths[b];
     const int len = (int)(len64 < 0 ? 0 : (len64 > P.T ? P.T : len64));
     const float* base = P.lp + (int64_t)b * P.sb;
@@ -432,7 +453,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
       load_chunk(0);
       if (nchunks > 1) load_chunk(1);
       wait_chunk(0);
-      condition_frame(chunk[0], P, lab2voc, fr[0], &sc->nc1[0]);
+      condition_frame(chunk[0], P, s_bias, s_tmin, lab2voc, fr[0], &sc->nc1[0]);
     }
     __syncthreads();
 
@@ -448,7 +469,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
             if (c + 1 < nchunks) load_chunk(c + 1);
             wait_chunk(c);
           }
-          condition_frame(chunk[c & 1] + r * P.V, P, lab2voc, fr[tn & 1], &sc->nc1[tn & 1]);
+          condition_frame(chunk[c & 1] + r * P.V, P, s_bias, s_tmin, lab2voc, fr[tn & 1], &sc->nc1[tn & 1]);
         }
         bar_sync(BAR_FRAME, BM_THREADS);
         continue;
@@ -565,7 +586,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
       {
         double m = sc->wmax[0];
         for (int w = 1; w < BM_CONS / 32; ++w) m = sc->wmax[w] > m ? sc->wmax[w] : m;
-        cutoff = m + (double)P.prune;
+        cutoff = m + (double)s_prune;
       }
       // ---- phase 4b: compact entries that survive the relative prune (order preserved)
       {
@@ -609,8 +630,8 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
         for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
         cons_sync();
-        const double top = cutoff - (double)P.prune;
-        const double scale = P.prune < 0.f ? 256.0 / -(double)P.prune : 0.0;
+        const double top = cutoff - (double)s_prune;
+        const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
         for (int i = tid; i < n_alive; i += BM_CONS) {
           int b = (int)((top - ascore[i]) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
@@ -823,13 +844,13 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
           if (newb[p] > newb[best]) best = p;
         int n = A.len[best];
         unsigned nd = A.node[best];
-        int32_t* out = P.out_tok + (int64_t)b * P.T;
+        int32_t* out = P.out_tok + ob * P.T;
         if (n > 0 && A.last[best] == space_lbl) {  // trailing space is not part of the text
           nd = nodes[nd].x;
           --n;
         }
-        P.out_len[b] = n;
-        if (P.out_score) P.out_score[b] = len > 0 ? newb[best] : 0.0;
+        P.out_len[ob] = n;
+        if (P.out_score) P.out_score[ob] = len > 0 ? newb[best] : 0.0;
         for (int i = n - 1; i >= 0; --i) {
           const uint2 rec = nodes[nd];
           out[i] = lab2voc[rec.y];
@@ -872,36 +893,55 @@ static int beam_max_grid() {
 #endif
 }
 
+// Resident CTAs of a launch over `items` work items at capacity `width`: what the occupancy calculator gives for the
+// launch's shared-memory footprint, never more than there are items.  The workspace is sized from the same number
+// (the footprint is taken with the smaller of the two possible label counts, so it can only over-estimate the grid).
+static int beam_grid_for(int64_t items, int64_t V, int VL, int width, size_t* smem_out) {
+  const int TS = beam_table_slots(width), NCAND = beam_ncand_cap(width, VL);
+  const size_t smem = beam_smem_bytes(width, (int)V, VL, TS, NCAND);
+  if (smem_out) *smem_out = smem;
+  if (smem > 227 * 1024) return 0;
+  int grid = beam_grid(items, smem);
+  const int gmax = beam_max_grid();
+  return grid > gmax ? gmax : grid;
+}
+
 size_t beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int width) {
-  (void)V;
-  int64_t g = beam_max_grid();
-  if (B < g) g = B;
+  int g = beam_grid_for(B, V, (int)V - 1, width, nullptr);
+  if (g < 1) g = 1;
   return 256 + (size_t)g * (size_t)beam_node_cap(T, width) * sizeof(uint2);
 }
 
 int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths,
-                const int32_t* order, int blank, int pad, int space, float bias, int width, float prune, float tmin,
+                const int32_t* order, int blank, int pad, int space, const ssd_beam_setting* settings, int n_set,
                 int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (B == 0) return SSD_OK;
+  if (B == 0 || n_set == 0) return SSD_OK;
   BeamParams P;
   P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.lengths = lengths; P.order = order;
   P.blank = blank; P.pad = (pad >= 0 && pad < V) ? pad : -1; P.space = space;
-  P.bias = bias; P.prune = prune; P.tmin = tmin; P.W = width;
+  int width = 0;
+  P.n_set = n_set;
+  for (int i = 0; i < n_set; ++i) {
+    P.set_w[i] = settings[i].beam_width;
+    P.set_bias[i] = settings[i].blank_bias;
+    P.set_prune[i] = settings[i].beam_prune_logp;
+    P.set_tmin[i] = settings[i].token_min_logp;
+    width = settings[i].beam_width > width ? settings[i].beam_width : width;
+  }
+  P.W = width;
   P.out_tok = out_tok; P.out_len = out_len; P.out_score = out_score;
   P.VL = beam_vl(V, blank, P.pad);
   P.TS = beam_table_slots(width);
   P.NCAND = beam_ncand_cap(width, P.VL);
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
-  const size_t smem = beam_smem_bytes(width, (int)V, P.VL, P.TS, P.NCAND);
-  if (smem > 227 * 1024) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
+  size_t smem = 0;
+  const int grid = beam_grid_for(B * n_set, V, P.VL, width, &smem);
+  if (grid < 1) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
 #ifndef SSD_EMU
   cudaError_t e = cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
 #endif
-  int grid = beam_grid(B, smem);
-  const int gmax = beam_max_grid();
-  if (grid > gmax) grid = gmax;
   P.node_cap = beam_node_cap(T, width);
   const size_t need = 256 + (size_t)grid * (size_t)P.node_cap * sizeof(uint2);
   if (!ws || ws_bytes < need) return fail(SSD_ERR_WORKSPACE, "beam: workspace %zu bytes, need %zu", ws_bytes, need);

@@ -1,5 +1,7 @@
 // extern "C" entry points of libssd_ctc.so: argument validation, then one kernel launch each.
 // Declared in include/ssd_ctc.h.
+#include <cmath>
+
 #include "ssd_common.cuh"
 
 namespace ssd {
@@ -51,9 +53,31 @@ int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
   if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: blank=%d outside [0,%lld)", blank, (long long)V);
   if (beam_width < 1 || beam_width > SSD_MAX_BEAM) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam: beam_width=%d outside [1,%d]", beam_width, SSD_MAX_BEAM);
   if (!(beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: beam_prune_logp must be <= 0");
-  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, blank_bias, beam_width,
-                     beam_prune_logp, token_min_logp, out_tokens, out_lengths, out_scores, workspace, workspace_bytes,
-                     (cudaStream_t)stream);
+  ssd_beam_setting one;
+  one.beam_width = beam_width; one.beam_prune_logp = beam_prune_logp; one.blank_bias = blank_bias; one.token_min_logp = token_min_logp;
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, &one, 1, out_tokens, out_lengths,
+                     out_scores, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ssd_ctc_beam_grid(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                      const int64_t* lengths, const int32_t* order, int blank, int pad, int space,
+                      const ssd_beam_setting* settings, int n_settings, int32_t* out_tokens, int32_t* out_lengths,
+                      double* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("ssd_ctc_beam_grid", log_probs, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (n_settings < 0 || n_settings > SSD_MAX_BEAM_SETTINGS)
+    return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_grid: n_settings=%d outside [0,%d]", n_settings, SSD_MAX_BEAM_SETTINGS);
+  if (n_settings > 0 && !settings) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_grid: settings is NULL");
+  if (B > 0 && n_settings > 0 && (!lengths || !out_lengths || (T > 0 && !out_tokens))) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_grid: NULL lengths/output pointer");
+  if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_grid: blank=%d outside [0,%lld)", blank, (long long)V);
+  if (B * (int64_t)(n_settings > 0 ? n_settings : 1) > 2147483647LL) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_grid: B * n_settings exceeds 32-bit range");
+  for (int i = 0; i < n_settings; ++i) {
+    if (settings[i].beam_width < 1 || settings[i].beam_width > SSD_MAX_BEAM)
+      return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_grid: settings[%d].beam_width=%d outside [1,%d]", i, settings[i].beam_width, SSD_MAX_BEAM);
+    if (!(settings[i].beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_grid: settings[%d].beam_prune_logp must be <= 0", i);
+  }
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, settings, n_settings, out_tokens,
+                     out_lengths, out_scores, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t ssd_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
@@ -79,8 +103,57 @@ int ssd_ctc_loss(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
   if (tgt_stride < S_max) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: tgt_stride < S_max");
   if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: blank=%d outside [0,%lld)", blank, (long long)V);
   if (mean_denominator < 0) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss: mean_denominator < 0");
-  return loss_launch(log_probs, B, T, V, stride_b, stride_t, targets, tgt_stride, S_max, input_lengths, target_lengths, order, blank,
-                     zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, workspace_bytes, (cudaStream_t)stream);
+  return loss_launch(log_probs, nullptr, 0, B, T, V, stride_b, stride_t, targets, tgt_stride, S_max, input_lengths, target_lengths, order,
+                     blank, zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+static size_t lse_offset(int64_t B, int64_t T, int64_t V, int64_t S_max) { return (loss_workspace_bytes(B, T, V, S_max) + 255) & ~(size_t)255; }
+static int64_t lse_row_stride(int64_t T) { return (T + 7) & ~(int64_t)7; }  // a block of 8 frames = one aligned 32-byte bulk copy
+
+size_t ssd_ctc_loss_from_logits_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max) {
+  if (B <= 0 || T < 0 || V <= 0 || S_max < 0) return 256;
+  return lse_offset(B, T, V, S_max) + (size_t)B * (size_t)lse_row_stride(T) * sizeof(float) + 256;
+}
+
+int ssd_row_logsumexp(const float* x, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t, float* lse,
+                      int64_t lse_stride, void* stream) {
+  int rc = check_common("ssd_row_logsumexp", x, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (B > 0 && T > 0 && !lse) return fail(SSD_ERR_BAD_ARG, "ssd_row_logsumexp: lse is NULL");
+  if (lse_stride < T) return fail(SSD_ERR_BAD_ARG, "ssd_row_logsumexp: lse_stride < T");
+  return row_lse_launch(x, B, T, V, stride_b, stride_t, lse, lse_stride, (cudaStream_t)stream);
+}
+
+int ssd_ctc_loss_from_logits(const float* logits, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                             const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* input_lengths,
+                             const int64_t* target_lengths, const int32_t* order, int blank, int zero_infinity,
+                             int64_t mean_denominator, const float* grad_mul, float* nll, float* grad, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  int rc = check_common("ssd_ctc_loss_from_logits", logits, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (B > 0 && (!input_lengths || !target_lengths || !nll)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_from_logits: NULL lengths/nll pointer");
+  if (S_max < 0 || (S_max > 0 && B > 0 && !targets)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_from_logits: bad targets (S_max=%lld)", (long long)S_max);
+  if (S_max > SSD_MAX_TARGET) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_loss_from_logits: S_max=%lld exceeds SSD_MAX_TARGET=%d", (long long)S_max, SSD_MAX_TARGET);
+  if (tgt_stride < S_max) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_from_logits: tgt_stride < S_max");
+  if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_from_logits: blank=%d outside [0,%lld)", blank, (long long)V);
+  if (mean_denominator < 0) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_from_logits: mean_denominator < 0");
+  if (B == 0) return SSD_OK;
+  const size_t need = ssd_ctc_loss_from_logits_workspace_bytes(B, T, V, S_max);
+  if (!workspace || workspace_bytes < need) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss_from_logits: workspace %zu bytes, need %zu", workspace_bytes, need);
+  const size_t off = lse_offset(B, T, V, S_max);
+  float* lse = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + off);
+  const int64_t ls = lse_row_stride(T);
+  rc = row_lse_launch(logits, B, T, V, stride_b, stride_t, lse, ls, (cudaStream_t)stream);
+  if (rc) return rc;
+  return loss_launch(logits, lse, ls, B, T, V, stride_b, stride_t, targets, tgt_stride, S_max, input_lengths, target_lengths, order, blank,
+                     zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, off, (cudaStream_t)stream);
+}
+
+int ssd_scale_if(float* x, int64_t n, const float* g, float expected, void* stream) {
+  if (n < 0) return fail(SSD_ERR_BAD_ARG, "ssd_scale_if: n < 0");
+  if (n > 0 && (!x || !g)) return fail(SSD_ERR_BAD_ARG, "ssd_scale_if: NULL pointer");
+  if (!(expected != 0.f) || !(fabsf(expected) <= 3.0e38f)) return fail(SSD_ERR_BAD_ARG, "ssd_scale_if: expected must be finite and non-zero");
+  return scale_if_launch(x, n, g, expected, (cudaStream_t)stream);
 }
 
 int ssd_edit_counts(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* hyp_tok, const int64_t* hyp_off,

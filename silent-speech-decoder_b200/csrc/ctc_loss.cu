@@ -86,6 +86,8 @@ __device__ __forceinline__ double prob_of(float lp) {
 
 struct LossParams {
   const float* lp;
+  const float* lse;    // non-null: `lp` holds logits, lse[b * lse_stride + t] their per-frame log-sum-exp (row f-2)
+  int64_t lse_stride;
   int64_t T, sb, st;
   int B, V;
   const int64_t* targets;
@@ -378,15 +380,28 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
     tstamp(P, 2, pl.h, q, 0, uiter);
     const Prod pd = prod_desc(q, pl.h, pl.m_h, pl.m_o, K, pl.NP1, pl.NSEG);
     double* pR = reinterpret_cast<double*>(hf.p(slot));
+    // logits input: lane r holds the log-sum-exp of the block's row r (K <= 32), handed out by shuffle
+    float lse_r = 0.f;
+    {
+      const int t_lo = pd.dir ? pl.Tb - pd.tau0 - pd.n : pd.tau0;
+      if (P.lse && lane < pd.n) lse_r = P.lse[(int64_t)pl.b * P.lse_stride + t_lo + lane];
+    }
     // row r of the slot <-> local time tau0 + r of direction pd.dir
     if (P.use_tma) {
       const int rs = (int)(Q % LS_NRAW);
       warp_wait(&hf.bar[B_RAW + rs], (Q / LS_NRAW) & 1u);
       const float4* raw4 = reinterpret_cast<const float4*>(hf.raw(rs));
-      for (int idx = lane; idx < pd.n * V4; idx += 32) {  // V % 4 == 0 on this path
+      const int n_it = (pd.n * V4 + 31) / 32;
+      for (int it = 0; it < n_it; ++it) {  // V % 4 == 0 on this path
+        const int idx0 = it * 32 + lane;
+        const bool live = idx0 < pd.n * V4;
+        const int idx = live ? idx0 : 0;
         const int br = idx / V4, c4 = idx - br * V4;
         const int r = pd.dir ? pd.n - 1 - br : br;
-        const float4 v = raw4[idx];
+        const float ls = __shfl_sync(FULL, lse_r, br);
+        if (!live) continue;
+        float4 v = raw4[idx];
+        v.x -= ls; v.y -= ls; v.z -= ls; v.w -= ls;
         double2* dst = reinterpret_cast<double2*>(pR + r * VP + 4 * c4);
         dst[0] = make_double2(prob_of(v.x), prob_of(v.y));
         dst[1] = make_double2(prob_of(v.z), prob_of(v.w));
@@ -395,7 +410,8 @@ __device__ void loader_role(const LossParams& P, const Half& hf, const Plan& pl,
       const int t_lo = pd.dir ? pl.Tb - pd.tau0 - pd.n : pd.tau0;
       for (int r = 0; r < pd.n; ++r) {
         const int br = pd.dir ? pd.n - 1 - r : r;
-        for (int v = lane; v < V; v += 32) pR[r * VP + v] = prob_of(ld_stream(base + (int64_t)(t_lo + br) * P.st + v));
+        const float ls = __shfl_sync(FULL, lse_r, br);
+        for (int v = lane; v < V; v += 32) pR[r * VP + v] = prob_of(ld_stream(base + (int64_t)(t_lo + br) * P.st + v) - ls);
       }
     }
     if (lane < pd.n) pR[lane * VP + V] = 0.0;  // dummy column (K <= 32)
@@ -921,10 +937,10 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
 
 // fp32 fast path (ctc_loss_fast.cu)
 size_t loss_fast_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
-int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
-                     int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
-                     int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
-                     size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream);
+int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                     const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len,
+                     const int32_t* order, int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad,
+                     void* ws, size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream);
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -957,10 +973,10 @@ static int loss_launch_t(LossParams& P, const LossPlan& pl, cudaStream_t stream)
   return check_launch("loss_kernel");
 }
 
-int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
-                int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
-                int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
-                size_t ws_bytes, cudaStream_t stream) {
+int loss_launch(const float* lp, const float* lse, int64_t lse_stride, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len,
+                const int32_t* order, int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad,
+                void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (B == 0) return SSD_OK;
   LossPlan pl;
   if (!plan_for(B, T, V, S_max, pl))
@@ -975,7 +991,7 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
     if (fast_need) {
       if (ws_bytes < fast_off + fast_need)
         return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, fast_off + fast_need);
-      const int rc = loss_fast_launch(lp, B, T, V, sb, st, targets, tgt_stride, S_max, in_len, tg_len, order, blank, zero_inf, mean_den,
+      const int rc = loss_fast_launch(lp, lse, lse_stride, B, T, V, sb, st, targets, tgt_stride, S_max, in_len, tg_len, order, blank, zero_inf, mean_den,
                                       grad_mul, nll, grad, reinterpret_cast<unsigned char*>(ws) + fast_off, fast_need, &only, &only_count,
                                       stream);
       if (rc != SSD_OK && rc != SSD_ERR_UNSUPPORTED) return rc;
@@ -985,7 +1001,7 @@ int loss_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   if (only && env_int("SSD_LOSS_FASTONLY", 0)) return SSD_OK;  // timing experiments only: flagged rows stay unrecomputed
   LossParams P;
   P.only = only; P.only_count = only_count;
-  P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
+  P.lp = lp; P.lse = lse; P.lse_stride = lse_stride; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
   P.in_len = in_len; P.tg_len = tg_len; P.order = order;
   P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;

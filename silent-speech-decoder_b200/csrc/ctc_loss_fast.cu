@@ -94,6 +94,10 @@ constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
 constexpr int F_FR = SSD_F_FR;  // frames interleaved in the gradient stage
 constexpr int F_TOP = 40;  // renormalised strips have their largest cell in [2^40, 2^41)
 constexpr int F_SPAD = 256;  // label staging capacity (S <= 255 on this path)
+#ifndef SSD_F_REBASE
+#define SSD_F_REBASE 32
+#endif
+constexpr int F_REBASE = SSD_F_REBASE;  // a live neighbour this many binades above me: take its exponent (my cells shrink, its inflow stays finite)
 constexpr float F_MASS_TOL = 1.5e-5f;
 constexpr float F_LP_ABS = 80.f;  // log-probs beyond +-80 (or NaN) send the utterance to the exact path
 
@@ -143,6 +147,8 @@ __device__ __forceinline__ float warp_sum_fx(float v) {
 
 struct FastParams {
   const float* lp;
+  const float* lse;    // non-null: `lp` holds LOGITS and lse[b * lse_stride + t] their per-frame log-sum-exp (row f-2)
+  int64_t lse_stride;  // multiple of F_K: a block's F_K values are one aligned 32-byte bulk copy
   int64_t T, sb, st;
   int B, V;
   const int64_t* targets;
@@ -194,7 +200,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(int V, int RS, int S_tab, i
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   FastSmem m;
   m.p_slot = al((size_t)(V + 1) * F_KS * 4 + 16);
-  m.raw_slot = al((size_t)F_K * V * 4);
+  m.raw_slot = al((size_t)F_K * V * 4 + F_K * 4);  // + the block's per-frame log-sum-exp values (logits input)
   m.main_bytes = F_NP * m.p_slot + F_NRAW * m.raw_slot;
   m.wrow_bytes = al((size_t)F_H * RS * 4);
   m.worker_bytes = m.wrow_bytes + m.p_slot + 2 * m.raw_slot;
@@ -444,7 +450,7 @@ __device__ __forceinline__ void fstep(FStrip<NC>& s, Inflow& in, const FLabels<N
 // than either side can hold next to values of up to 2^(TOP+14)
 __device__ __forceinline__ int scale_split(int qe) {
   int h = qe >> 1;
-  const int cap = 126 - (F_TOP + 14);
+  const int cap = 126 - (F_TOP + 14 + F_REBASE);  // a strip's cells reach 2^(TOP+14) on their own, times the inflow factor
   h = h < qe - cap ? qe - cap : h;
   return h > cap ? cap : h;
 }
@@ -479,28 +485,58 @@ __device__ __forceinline__ bool renorm_exchange(FStrip<NC>& s) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) s.x[i] *= f;
   s.e += k;
-  // an empty strip takes the exponent of the nearest live strip on the side its mass will come from
+  // Strips DOWNSTREAM of the strip with the largest basis (the mass front, or the bulk) whose own basis is more than
+  // F_REBASE binades below it take that basis: whatever reaches them during the coming block comes from there, and
+  // an inflow factor of at most 2^F_REBASE is what the products downstream (Z, posteriors) are dimensioned for.
+  // Their own cells shrink by an exact power of two; what underflows was 2^-166 of the front.  One REDUX and one
+  // ballot, no loop: with confident posteriors the front is a cliff of ~2^150 per strip, several strips wide.
   const unsigned lv = __ballot_sync(FULL, live);
+  {
+    const int G = __reduce_max_sync(FULL, live ? s.e : -(1 << 30));
+    const unsigned top = __ballot_sync(FULL, live && s.e == G);
+    const bool down = DIR == 0 ? (top & ((1u << lane) - 1u)) != 0u : (lane < 31 && (top >> (lane + 1)) != 0u);
+    const int gap = G - s.e;
+    if (live && down && gap > F_REBASE) {
+      const float g = pow2c(-gap);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) s.x[i] *= g;
+      s.e = G;
+    }
+  }
+  // an empty strip takes the exponent of the nearest live strip on the side its mass will come from
   int src;
+  bool fed;  // some strip on the side my mass comes from is live: my neighbour's exponent is that of real values
   if (DIR == 0) {
     const unsigned below = lv & ((1u << lane) - 1u);
     src = below ? 31 - __clz((int)below) : lane;
+    fed = below != 0u;
   } else {
     const unsigned above = lane == 31 ? 0u : (lv >> (lane + 1)) << (lane + 1);
     src = above ? __ffs((int)above) - 1 : lane;
+    fed = above != 0u;
   }
   const int e_near = __shfl_sync(FULL, s.e, src);
   if (!live) s.e = e_near;
-  // a live neighbour that dwarfs me: rebase on it so that its boundary cells stay representable
-  const int e_nb = DIR == 0 ? __shfl_up_sync(FULL, s.e, 1) : __shfl_down_sync(FULL, s.e, 1);
-  const int nb = DIR == 0 ? lane - 1 : lane + 1;
-  const bool nb_live = nb >= 0 && nb < 32 && ((lv >> (nb & 31)) & 1u);
-  const int d = e_nb - s.e;
-  if (nb_live && d > 100) {
-    const float g = pow2c(-d);
+  // What the rule above leaves (profiles with a second, lower hump): a neighbour on the feeding side whose basis
+  // dwarfs mine -- rebase on it, so that whatever it hands over during the coming block stays finite in my basis.
+  // The neighbour itself may be empty right now: it then carries the exponent of the live strip beyond it and is a
+  // conduit (an empty strip fills up within the block; its outflow overflowed a strip that had kept a basis 2^199
+  // lower: peaked posteriors on their own transcript, i.e. every trained model, were flagged for that).  A
+  // neighbour with nothing live behind it is stale and never rebased on.  A strip that rebases widens its own
+  // downstream neighbour's gap, so the test repeats until no strip moves: one vote and no work almost always.
+  int e_nb = 0;
+#pragma unroll 1
+  for (int round = 0; round < 32; ++round) {
+    e_nb = DIR == 0 ? __shfl_up_sync(FULL, s.e, 1) : __shfl_down_sync(FULL, s.e, 1);
+    const int d = e_nb - s.e;
+    const bool move = fed && d > F_REBASE;
+    if (!__any_sync(FULL, move)) break;
+    if (move) {
+      const float g = pow2c(-d);
 #pragma unroll
-    for (int i = 0; i < NC; ++i) s.x[i] *= g;
-    s.e = e_nb;
+      for (int i = 0; i < NC; ++i) s.x[i] *= g;
+      s.e = e_nb;
+    }
   }
   set_fin<NC, DIR>(s, s.e);
   return ok;
@@ -558,9 +594,9 @@ __device__ __forceinline__ int block_order(int i, int NB, int Tb) {
 // shared memory ([n][V], TMA-loaded) or, if null, `graw` the same rows in global memory (row stride st).
 // One (frame quad, class) item per lane and pass: four independent load -> exp chains in flight, small code.
 // Returns non-zero if a value outside +-F_LP_ABS (or NaN) was seen (D1).
-template <bool SMEM>
+template <bool SMEM, bool LOGITS>
 __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
-                                               float* __restrict__ pblk) {
+                                               float* __restrict__ pblk, const float* __restrict__ lse) {
   const int lane = lane_id();
   float amax = 0.f;  // largest |log-prob| seen (a NaN passes here and poisons Z or a frame's mass instead)
   SSD_UNROLL(SSD_F_CU)
@@ -576,6 +612,9 @@ __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, co
       int r = hq * 4 + j;
       r = r < n ? r : n - 1;  // rows beyond a partial block: re-read the last one, masked below
       lp[j] = SMEM ? raw[r * V + v] : ld_stream(graw + (int64_t)r * st + v);
+      // logits: log-prob = x - lse_t.  The F_K values sit behind the rows in the landing buffer (SMEM) or are read
+      // from the global array
+      if (LOGITS) lp[j] -= SMEM ? raw[F_K * V + r] : ld_cg(lse + r);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -594,9 +633,12 @@ __device__ __forceinline__ int convert_block_t(const float* __restrict__ raw, co
 // one loop per source: the unused path's address arithmetic would otherwise ride along predicated off.
 // NOT inlined: loaders and workers then run one shared copy, which is what the instruction cache wants
 // (the kernel is instruction-fetch sensitive: four different roles issue from every sub-partition).
+// `lse` non-null selects the logits variants (global pointer to the block's first frame; with `raw` set the
+// values are taken from the landing buffer instead, where a second bulk copy has put them).
 __device__ __noinline__ int convert_block(const float* __restrict__ raw, const float* __restrict__ graw, int64_t st, int n, int V,
-                                             float* __restrict__ pblk) {
-  return raw ? convert_block_t<true>(raw, graw, st, n, V, pblk) : convert_block_t<false>(raw, graw, st, n, V, pblk);
+                                             float* __restrict__ pblk, const float* __restrict__ lse) {
+  if (lse) return raw ? convert_block_t<true, true>(raw, graw, st, n, V, pblk, lse) : convert_block_t<false, true>(raw, graw, st, n, V, pblk, lse);
+  return raw ? convert_block_t<true, false>(raw, graw, st, n, V, pblk, lse) : convert_block_t<false, false>(raw, graw, st, n, V, pblk, lse);
 }
 
 struct MainView {  // one main's rings
@@ -613,14 +655,16 @@ __device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan
   const int lane = lane_id();
   const int V = P.V;
   const float* base = P.lp + (int64_t)pl.b * P.sb;
+  const float* lse_base = P.lse ? P.lse + (int64_t)pl.b * P.lse_stride : nullptr;
   auto blk_of = [&](int bi) { return DIR ? pl.NB - 1 - bi : bi; };
   auto issue_raw = [&](int bi) {  // lane 0
     const int q = blk_of(bi);
     const int n = min(F_K, pl.Tb - q * F_K);
     const int slot = (int)((qbase + (unsigned)bi) % F_NRAW);
     const uint32_t bytes = (uint32_t)(n * V * 4);
-    mbar_arrive_expect_tx(&mv.bar[FB_RAW + slot], bytes);
+    mbar_arrive_expect_tx(&mv.bar[FB_RAW + slot], bytes + (lse_base ? F_K * 4u : 0u));
     bulk_g2s(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot]);
+    if (lse_base) bulk_g2s(mv.raw(slot) + F_K * V, lse_base + q * F_K, F_K * 4u, &mv.bar[FB_RAW + slot]);
   };
   // The rows come from HBM the first time (~1.5 us per bulk copy, measured: with F_NRAW - 1 = 2 copies in flight the
   // ring delivered one block per ~1470 cycles and the sweeps starved).  A bulk L2 prefetch F_PFD blocks ahead costs
@@ -660,7 +704,7 @@ __device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan
       raw = mv.raw(rs);
     }
     fstamp(P, uiter, bi, 2);
-    lpbad |= convert_block(raw, base + (int64_t)q * F_K * P.st, P.st, n, V, mv.p(slot));
+    lpbad |= convert_block(raw, base + (int64_t)q * F_K * P.st, P.st, n, V, mv.p(slot), lse_base ? lse_base + q * F_K : nullptr);
     __syncwarp();
     if (lane == 0) mbar_arrive(&mv.bar[FB_PFULL + slot]);
     fstamp(P, uiter, bi, 3);
@@ -743,6 +787,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
   const unsigned char* ck_a = ckpt_cta;
   const unsigned char* ck_b = ckpt_cta + (size_t)P.nb_max * P.ckpt_rec_bytes;
   const float* lp_base = P.lp + (int64_t)pl.b * P.sb;
+  const float* lse_base = P.lse ? P.lse + (int64_t)pl.b * P.lse_stride : nullptr;
   float* g_base = want_grad ? P.grad + (int64_t)pl.b * P.sb : nullptr;
   const float scale = sc->scale;
   bool mass_ok = true;
@@ -765,8 +810,9 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     const int q = block_order(i, pl.NB, pl.Tb);
     const int n = min(F_K, pl.Tb - q * F_K);
     const uint32_t bytes = (uint32_t)(n * V * 4);
-    mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes);
+    mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes + (lse_base ? F_K * 4u : 0u));
     bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
+    if (lse_base) bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride + F_K * V, lse_base + q * F_K, F_K * 4u, &wv.rawbar[use & 1u]);
   };
   if (!late) bar_sync(1, 32 * (F_W + 2));  // released by the two mains shortly before the first block can be ready
   int i = grab();
@@ -788,7 +834,7 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
       raw = wv.raw0 + (nraw & 1u) * wv.raw_stride;
     }
     ++nraw;
-    convert_block(raw, lp_base + (int64_t)t0 * P.st, P.st, n, V, pblk);
+    convert_block(raw, lp_base + (int64_t)t0 * P.st, P.st, n, V, pblk, lse_base ? lse_base + t0 : nullptr);
     fstamp(P, uiter, nmine, 1);
     mbar_wait_relaxed(&blk_ready[q], uiter & 1u);  // both checkpoints of the block are published
     fstamp(P, uiter, nmine, 2);
@@ -865,15 +911,28 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
           for (int k = 0; k < NC / 2; ++k) pc.lab[k] = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(pblk) + la.off[k]);
           fstep<NC, 0, false>(z, zin, la, pc, nullptr);
           const float2* src = reinterpret_cast<const float2*>(rows) + lane;
+          // both factors may sit 2^F_REBASE above their strips' nominal top (inflow from a higher basis during the
+          // block): each side is brought to a top of 2^F_TOP by an exact power of two before the products, and the
+          // lane's exponent takes the two shifts back (once per utterance: the cost is nothing)
+          float ma = 0.f, mb = 0.f;
+#pragma unroll
+          for (int k = 0; k < NC / 2; ++k) {
+            const float2 w = src[k * 32];
+            ma = fmaxf(ma, fmaxf(z.x[2 * k], z.x[2 * k + 1]));
+            mb = fmaxf(mb, fmaxf(w.x, w.y));
+          }
+          const int ka = ma >= 1.17549435e-38f && ma < 3.0e38f ? expo_f(ma) - F_TOP : 0;
+          const int kb = mb >= 1.17549435e-38f && mb < 3.0e38f ? expo_f(mb) - F_TOP : 0;
+          const float da = pow2c(-ka), db = pow2c(-kb);
           float sl = 0.f;
 #pragma unroll
           for (int k = 0; k < NC / 2; ++k) {
             const float2 w = src[k * 32];
-            sl = fmaf(z.x[2 * k], w.x, sl);
-            sl = fmaf(z.x[2 * k + 1], w.y, sl);
+            sl = fmaf(z.x[2 * k] * da, w.x * db, sl);
+            sl = fmaf(z.x[2 * k + 1] * da, w.y * db, sl);
           }
           const bool okl = sl >= 1.17549435e-38f && sl < 3.0e38f;
-          const int q_l = e_alpha + e_beta;
+          const int q_l = e_alpha + e_beta + ka + kb;
           const int key = okl ? q_l + expo_f(sl) : -(1 << 30);
           const int Qm = __reduce_max_sync(FULL, key);
           const bool bad_lane = !(sl >= 0.f && sl < 3.0e38f);  // NaN / inf somewhere
@@ -1309,15 +1368,15 @@ static int loss_fast_launch_t(FastParams& P, const FastPlan& pl, cudaStream_t st
 
 // Returns SSD_OK and sets *flags / *nflag (device pointers into ws) when the fast path ran,
 // SSD_ERR_UNSUPPORTED (without touching the error text) when it does not apply.
-int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* targets,
-                     int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len, const int32_t* order,
-                     int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad, void* ws,
-                     size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream) {
+int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                     const int64_t* targets, int64_t tgt_stride, int64_t S_max, const int64_t* in_len, const int64_t* tg_len,
+                     const int32_t* order, int blank, int zero_inf, int64_t mean_den, const float* grad_mul, float* nll, float* grad,
+                     void* ws, size_t ws_bytes, const int** flags, const unsigned** nflag, cudaStream_t stream) {
   FastPlan pl;
   if (!fast_plan_for(B, T, V, S_max, pl)) return SSD_ERR_UNSUPPORTED;
   if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
   FastParams P;
-  P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
+  P.lp = lp; P.lse = lse; P.lse_stride = lse_stride; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
   P.in_len = in_len; P.tg_len = tg_len; P.order = order;
   P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;
@@ -1330,6 +1389,7 @@ int loss_fast_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t s
   P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nb_max = pl.nb_max;
   P.RS = pl.RS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
+  if (lse && !(aligned16(lse) && lse_stride % F_K == 0)) P.use_tma = 0;
   if (fast_env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;
   P.rotate = fast_env_int("SSD_LOSS_NOROT", 0) ? 0 : 1;
   {

@@ -100,12 +100,10 @@ int edit_launch(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* h
   const int edge_stride = max_hyp_len > ED_TILE ? (int)max_ref_len + 1 : 0;
   const size_t smem = (size_t)ED_WARPS * edge_stride * sizeof(int);
 #ifndef SSD_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the current device, and one process may drive several
     cudaError_t e = cudaFuncSetAttribute(edit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ED_WARPS * (SSD_MAX_EDIT_LEN + 1) * (int)sizeof(int));
     if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "edit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
 #endif
   const unsigned grid = (unsigned)((N + ED_WARPS - 1) / ED_WARPS);

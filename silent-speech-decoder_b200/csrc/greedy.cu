@@ -76,21 +76,34 @@ __global__ void __launch_bounds__(GR_THREADS) greedy_kernel(const float* __restr
     // so each lane starts at a different 16-byte chunk to spread the banks.
     int best_i = -1;
     if (tid < rows) {
-      float* row = tile + tid * V;
-      if (bias != 0.f && blank >= 0 && blank < V) row[blank] += bias;  // my own row: no hazard
+      const float* row = tile + tid * V;
+      // the blank bias is applied to the VALUE as it is compared (ctc.py:18-20 adds it to a clone): the tile is
+      // never written by the generic proxy, so the next bulk copy into this buffer needs no cross-proxy fence
+      const bool biased = bias != 0.f && blank >= 0 && blank < V;
       if ((V & 3) == 0) {
         const float4* row4 = reinterpret_cast<const float4*>(row);
         const int V4 = V >> 2;
+        const int cb = biased ? (blank >> 2) : -1, jb = blank & 3;
+        auto fetch = [&](int c) {
+          float4 x = row4[c];
+          if (c == cb) {
+            if (jb == 0) x.x += bias;
+            else if (jb == 1) x.y += bias;
+            else if (jb == 2) x.z += bias;
+            else x.w += bias;
+          }
+          return x;
+        };
         int c = tid % V4;
         float m = -INFINITY;
         for (int j = 0; j < V4; ++j) {
-          const float4 x = row4[c];
+          const float4 x = fetch(c);
           m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
           c = (c + 1 == V4) ? 0 : c + 1;
         }
         int bi = 0x7fffffff;
         for (int j = 0; j < V4; ++j) {
-          const float4 x = row4[c];
+          const float4 x = fetch(c);
           const int i0 = 4 * c;
           // highest index first so that the lowest matching one is what remains
           int k = x.w == m ? i0 + 3 : 0x7fffffff;
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(GR_THREADS) greedy_kernel(const float* __restr
       } else {
         float best = 0.f;
         for (int v = 0; v < V; ++v) {
-          const float x = row[v];
+          const float x = row[v] + ((biased && v == blank) ? bias : 0.f);
           if (best_i < 0 || x > best) {
             best = x;
             best_i = v;
@@ -146,11 +159,9 @@ int greedy_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, 
   // bulk copies need contiguous rows and 16-byte aligned tile starts and sizes
   const int use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
 #ifndef SSD_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the current device, and one process may drive several
     cudaError_t e = cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GR_THREADS * SSD_MAX_VOCAB * 4);
     if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "greedy: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
 #endif
   SSD_LAUNCH(greedy_kernel, (unsigned)B, GR_THREADS, smem, stream, lp, T, (int)V, sb, st, lengths, blank, bias, out_tok, out_len,

@@ -106,6 +106,10 @@ class Evaluator:
 
     def add(self, utterance_ids: Iterable, transcripts: Sequence[str], log_probs: torch.Tensor, lengths: torch.Tensor) -> List[str]:
         hyps = self.decoder(log_probs, lengths)  # device tensors go straight to the kernel: no .cpu() hop
+        return self.add_decoded(utterance_ids, transcripts, hyps)
+
+    def add_decoded(self, utterance_ids: Iterable, transcripts: Sequence[str], hyps: Sequence[str]) -> List[str]:
+        """Record transcripts that were decoded elsewhere (the grid evaluator's single launch, a sharded decode)."""
         for uid, ref, hyp in zip(utterance_ids, transcripts, hyps):
             self.refs.append(ref)
             self.hyps.append(hyp)
@@ -172,24 +176,51 @@ class DecoderSetting:
 
 
 class GridEvaluator:
-    """Every setting of a decoder grid over the same batches, log-probs moved to the GPU once per batch.
+    """Every setting of a decoder grid over the same batches: log-probs are moved to the GPU once per batch and ALL
+    beam settings of the grid are decoded by ONE kernel launch (``ssd_ctc_beam_grid``: a work item is
+    (setting, utterance)); greedy settings take one greedy launch each.  The reference runs its whole evaluation --
+    encoder included -- once per setting (``orchestrate.py:129-153,235-249``).
 
     Settings that ask for a language model are reported under ``skipped`` (the LM is outside this path; the
     reference skips them too when the ARPA file is missing, ``orchestrate.py:117-119``)."""
 
+    MAX_PER_LAUNCH = 8  # SSD_MAX_BEAM_SETTINGS
+
     def __init__(self, vocab: Vocab, grid: Sequence[DecoderSetting]):
+        from ..decoding import ctc as _ctc
+
         names = [g.name for g in grid]
         if len(set(names)) != len(names):
             raise ValueError(f"decoder setting names must be unique: {names}")
+        self.vocab = vocab
         self.skipped = [g.name for g in grid if g.use_lm]
-        self.evaluators: Dict[str, Evaluator] = {g.name: Evaluator(g.build(vocab), g.resolved()) for g in grid if not g.use_lm}
+        self.settings = [g for g in grid if not g.use_lm]
+        self.evaluators: Dict[str, Evaluator] = {g.name: Evaluator(g.build(vocab), g.resolved()) for g in self.settings}
+        self._beam_text, self._space = _ctc._beam_label_strings(vocab)
+        self._pad = vocab.pad_id if (vocab.pad_id != vocab.blank_id and 0 <= vocab.pad_id < vocab.size) else -1
+        self._rows_to_strings = _ctc._rows_to_strings
 
     def add(self, utterance_ids: Iterable, transcripts: Sequence[str], log_probs: torch.Tensor, lengths: torch.Tensor) -> Dict[str, List[str]]:
         dev = ops._device(log_probs)
         lp = log_probs.detach().to(dev, non_blocking=True)  # one host->device copy shared by all settings
         ln = torch.as_tensor(lengths).to(dev, non_blocking=True)
         ids = list(utterance_ids)
-        return {name: e.add(ids, transcripts, lp, ln) for name, e in self.evaluators.items()}
+        out: Dict[str, List[str]] = {}
+        beams = [g for g in self.settings if g.method.lower() == "beam"]
+        for lo in range(0, len(beams), self.MAX_PER_LAUNCH):
+            part = beams[lo: lo + self.MAX_PER_LAUNCH]
+            spec = []
+            for g in part:
+                r = g.resolved()
+                spec.append((int(r["beam_width"]), float(r["beam_prune_logp"]), float(g.blank_bias), -5.0))
+            tok, cnt, _ = ops.beam_grid_ids(lp, ln, self.vocab.blank_id, self._pad, self._space, spec)
+            for i, g in enumerate(part):
+                hyps = self._rows_to_strings(tok[i], cnt[i], self._beam_text, normalise_space=True)
+                out[g.name] = self.evaluators[g.name].add_decoded(ids, transcripts, hyps)
+        for g in self.settings:
+            if g.method.lower() != "beam":
+                out[g.name] = self.evaluators[g.name].add(ids, transcripts, lp, ln)
+        return out
 
     def finish(self, out_root=None, **kw) -> Dict[str, Dict]:
         """-> {setting name: metrics}; with ``out_root`` each setting also gets ``<out_root>/<name>/`` files."""

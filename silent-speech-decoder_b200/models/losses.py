@@ -37,36 +37,78 @@ def _check_host_lengths(name: str, t: torch.Tensor, limit: int, what: str) -> No
             raise RuntimeError(f"Expected {name} to have value at most {limit}, but got value {hi} ({what})")
 
 
-class _CTCNll(torch.autograd.Function):
-    """(T,B,V) log-probs -> per-utterance nll (B,).  Forward runs the fused kernel once and keeps
-    d nll_b / d log_probs; backward only scales it by the incoming per-utterance gradient."""
+def _dense(t: torch.Tensor) -> bool:
+    """True when the tensor covers its storage range without holes or overlap (any permutation of a contiguous one)."""
+    sizes_strides = sorted(((st, sz) for sz, st in zip(t.shape, t.stride()) if sz > 1))
+    expect = 1
+    for st, sz in sizes_strides:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+class _CTCFused(torch.autograd.Function):
+    """(T,B,V) log-probs (or logits) -> the REDUCED loss, forward and backward in the one fused launch of forward.
+
+    The kernel writes d loss / d input already scaled for the reduction ('mean': 1 / (B * max(S_b,1)) per utterance,
+    in-kernel) and by ``expect`` -- the upstream scalar the caller knows it will receive (``lambda_ctc`` when the
+    loss is used as at losses.py:104-105).  backward then hands the buffer out as it is: the incoming scalar is
+    compared with ``expect`` on the device (``ssd_scale_if``) and the gradient is rescaled in place only if they
+    differ.  No host synchronisation, no extra pass over the (B,T,V) gradient in the common case.
+    reduction 'none' keeps a per-utterance incoming gradient and multiplies row-wise."""
 
     @staticmethod
-    def forward(ctx, log_probs_tbv, targets, input_lengths, target_lengths, blank: int, zero_infinity: bool):
+    def forward(ctx, x_tbv, targets, input_lengths, target_lengths, blank: int, zero_infinity: bool, reduction: str,
+                from_logits: bool, expect: float):
         need = ctx.needs_input_grad[0]
-        x = log_probs_tbv.transpose(0, 1)  # (B,T,V) view of the same memory, no copy
-        nll, grad = ops.ctc_loss_fwd_bwd(x, input_lengths, targets, target_lengths, blank=blank,
-                                         zero_infinity=zero_infinity, mean_denominator=0, want_grad=need)
-        ctx.in_dtype = log_probs_tbv.dtype
-        ctx.in_device = log_probs_tbv.device
-        if need:
-            ctx.save_for_backward(grad)
-        out = nll.to(log_probs_tbv.dtype)
-        return out if out.device == log_probs_tbv.device else out.to(log_probs_tbv.device)
+        x = x_tbv.transpose(0, 1)  # (B,T,V) view of the same memory, no copy
+        B = x.size(0)
+        expect = float(expect) if (expect and reduction != "none") else 1.0
+        gm = None
+        if need and expect != 1.0:
+            gm = ops.device_scalar(ops._device(x), expect)
+        nll, grad = ops.ctc_loss_fwd_bwd(x, input_lengths, targets, target_lengths, blank=blank, zero_infinity=zero_infinity,
+                                         mean_denominator=B if reduction == "mean" else 0, want_grad=need, grad_mul=gm,
+                                         from_logits=from_logits)
+        ctx.in_dtype, ctx.in_device, ctx.reduction, ctx.expect = x_tbv.dtype, x_tbv.device, reduction, expect
+        ctx.grad_btv, ctx.applied = grad, None
+        if reduction == "none":
+            out = nll
+        elif reduction == "sum":
+            out = nll.sum()
+        else:
+            out = (nll / target_lengths.to(device=nll.device).clamp_min(1).to(nll.dtype)).mean()
+        out = out.to(x_tbv.dtype)
+        return out if out.device == x_tbv.device else out.to(x_tbv.device)
 
     @staticmethod
-    def backward(ctx, g_nll):
-        (grad_btv,) = ctx.saved_tensors
-        g = g_nll.to(device=grad_btv.device, dtype=torch.float32).view(-1, 1, 1)
-        out = (grad_btv * g).transpose(0, 1)  # back to (T,B,V)
+    def backward(ctx, g):
+        grad = ctx.grad_btv
+        if ctx.reduction == "none":
+            out = grad * g.to(device=grad.device, dtype=torch.float32).view(-1, 1, 1)
+        else:
+            g = g.to(device=grad.device, dtype=torch.float32).reshape(1)
+            if ctx.applied is None and _dense(grad):
+                ops.scale_if(grad, g, ctx.expect)  # no-op on the device when g is what forward scaled by
+                ctx.applied = g
+                out = grad
+            else:  # backward through the same graph again (retain_graph), or an input layout with holes
+                base = ctx.applied if ctx.applied is not None else torch.full_like(g, ctx.expect)
+                out = grad * (g / base)
+        out = out.transpose(0, 1)  # back to (T,B,V)
         if out.dtype != ctx.in_dtype or out.device != ctx.in_device:
             out = out.to(device=ctx.in_device, dtype=ctx.in_dtype)
-        return out, None, None, None, None, None
+        return out, None, None, None, None, None, None, None, None
 
 
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank: int = 0, reduction: str = "mean",
-             zero_infinity: bool = False) -> torch.Tensor:
-    """``torch.nn.functional.ctc_loss`` semantics on the native kernel.  log_probs: (T,B,V)."""
+             zero_infinity: bool = False, from_logits: bool = False, expect_grad: float = 1.0) -> torch.Tensor:
+    """``torch.nn.functional.ctc_loss`` semantics on the native kernel.  log_probs: (T,B,V).
+
+    ``from_logits`` (scope row f-2): the input is the CTC head's pre-softmax output (``heads.py:36``); the result is
+    the loss of ``log_softmax(input)`` and the gradient is taken with respect to the logits, without the log-prob
+    tensor ever existing.  ``expect_grad``: the scalar the caller expects autograd to send back (see _CTCFused)."""
     if log_probs.dim() == 2:  # unbatched (T,V), as torch accepts
         log_probs = log_probs.unsqueeze(1)
         targets = targets.unsqueeze(0) if targets.dim() == 1 else targets
@@ -79,6 +121,8 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank: int = 0, 
         raise RuntimeError(f"log_probs must be (T, N, C); got {tuple(log_probs.shape)}")
     if log_probs.dtype not in (torch.float32, torch.float64):
         raise RuntimeError(f'"ctc_loss" not implemented for {log_probs.dtype}')
+    if reduction not in ("none", "sum", "mean"):
+        raise ValueError(f"{reduction} is not a valid value for reduction")
     T, B, V = log_probs.shape
     input_lengths = torch.as_tensor(input_lengths)
     target_lengths = torch.as_tensor(target_lengths)
@@ -89,33 +133,33 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank: int = 0, 
     _check_host_lengths("input_lengths", input_lengths, T, "the time dimension of log_probs")
     if targets.dim() == 2:
         _check_host_lengths("target_lengths", target_lengths, targets.size(1), "the width of targets")
-    nll = _CTCNll.apply(log_probs, targets, input_lengths, target_lengths, int(blank), bool(zero_infinity))
-    if reduction == "none":
-        return nll[0] if unbatched else nll
-    if reduction == "sum":
-        return nll.sum()
-    if reduction == "mean":
-        tl = target_lengths.to(device=nll.device).clamp_min(1).to(nll.dtype)
-        return (nll / tl).mean()
-    raise ValueError(f"{reduction} is not a valid value for reduction")
+    out = _CTCFused.apply(log_probs, targets, input_lengths, target_lengths, int(blank), bool(zero_infinity), reduction,
+                          bool(from_logits), float(expect_grad))
+    if reduction == "none" and unbatched:
+        return out[0]
+    return out
 
 
 class CTCLoss(nn.Module):
     """``torch.nn.CTCLoss`` call shape: ``(log_probs (T,B,V), targets, input_lengths, target_lengths)``."""
 
-    def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False):
+    def __init__(self, blank: int = 0, reduction: str = "mean", zero_infinity: bool = False, from_logits: bool = False):
         super().__init__()
-        self.blank, self.reduction, self.zero_infinity = blank, reduction, zero_infinity
+        self.blank, self.reduction, self.zero_infinity, self.from_logits = blank, reduction, zero_infinity, from_logits
+        self.expect_grad = 1.0  # set by the owner when it knows the upstream scalar (DistillationCTCLoss: lambda_ctc)
 
     def forward(self, log_probs, targets, input_lengths, target_lengths):
-        return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction, self.zero_infinity)
+        return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction, self.zero_infinity,
+                        from_logits=self.from_logits, expect_grad=self.expect_grad)
 
 
 class DistillationCTCLoss(nn.Module):
-    def __init__(self, vocab_size: int, blank_id: int, weights: LossWeights, normalize_distill: bool = False):
+    def __init__(self, vocab_size: int, blank_id: int, weights: LossWeights, normalize_distill: bool = False,
+                 from_logits: bool = False):
         super().__init__()
         del vocab_size  # accepted and unused, as in the reference (losses.py:20-30)
-        self.ctc_loss = CTCLoss(blank=blank_id, zero_infinity=True)
+        # from_logits (not in the reference, scope row f-2): `log_probs` is then the head's pre-softmax output
+        self.ctc_loss = CTCLoss(blank=blank_id, zero_infinity=True, from_logits=from_logits)
         self.weights = weights  # reassigned from outside every epoch (train.py:486-489)
         self.normalize_distill = normalize_distill
 
@@ -131,6 +175,8 @@ class DistillationCTCLoss(nn.Module):
     ) -> Dict[str, torch.Tensor]:
         # (B,T,V) -> (T,B,V) view; lengths stay where they are (the reference moves them to the
         # host for ATen, losses.py:55 -- the native kernel reads them on the device)
+        # total = lambda_ctc * ctc + ...: autograd will send lambda_ctc back; the kernel scales by it up front
+        self.ctc_loss.expect_grad = float(self.weights.lambda_ctc) or 1.0
         ctc = self.ctc_loss(log_probs.transpose(0, 1), targets, logit_lengths, target_lengths)
         distill = torch.tensor(0.0, device=log_probs.device)
         if teacher_repr is not None:

@@ -9,14 +9,19 @@ CPU path.
 
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
 from . import _native
 
-_WS: Dict[Tuple[int, str], torch.Tensor] = {}
-LAUNCHES = {"greedy": 0, "beam": 0, "loss": 0, "edit": 0}  # kernels launched by this process (bench reads it)
+# One scratch buffer per (device, stream, kind): two streams (or two threads, each with its own current stream)
+# never share checkpoints, work-queue counters or back-pointer nodes.  Work on ONE stream is ordered, so reuse
+# across calls on that stream is safe; a buffer that has to grow is replaced, and the old one is returned to
+# torch's caching allocator, which only hands it out again to work queued on the same stream.
+_WS: Dict[Tuple[int, int, str], torch.Tensor] = {}
+_LAST_LOSS_WS: Dict[int, torch.Tensor] = {}
+LAUNCHES = {"greedy": 0, "beam": 0, "loss": 0, "edit": 0, "aux": 0}  # kernels launched by this process (bench reads it)
 
 
 def _device(t: torch.Tensor) -> torch.device:
@@ -30,11 +35,15 @@ def _device(t: torch.Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _dev_index(dev: torch.device) -> int:
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
 def _workspace(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind)
+    key = (_dev_index(dev), int(torch.cuda.current_stream(dev).cuda_stream), kind)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)  # allocated on (and owned by) the current stream
         _WS[key] = buf
     return buf
 
@@ -125,6 +134,93 @@ def beam_ids(
     return tok, cnt, score
 
 
+def beam_grid_ids(
+    log_probs: torch.Tensor,
+    lengths: torch.Tensor,
+    blank: int,
+    pad: int,
+    space: int,
+    settings: Sequence[Tuple[int, float, float, float]],
+    sort_by_length: bool = True,
+):
+    """Several decoder settings ``(beam_width, beam_prune_logp, blank_bias, token_min_logp)`` over the same batch in
+    ONE launch (``ssd_ctc_beam_grid``).  -> (tokens int32 (n,B,T), counts int32 (n,B), scores float64 (n,B)) on the
+    device, rows in the order of ``settings``."""
+    lib = _native.load()
+    dev = _device(log_probs)
+    n = len(settings)
+    if n > 8:
+        raise ValueError(f"at most 8 decoder settings per launch; got {n}")
+    with torch.cuda.device(dev):
+        x = _prep_log_probs(log_probs, dev)
+        B, T, V = x.shape
+        ln = _prep_lengths(lengths, B, dev)
+        tok = torch.empty((n, B, max(T, 1)), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((n, B), dtype=torch.int32, device=dev)
+        score = torch.zeros((n, B), dtype=torch.float64, device=dev)
+        if B and T and n:
+            sb, st = _strides(x)
+            # the kernel walks settings in array order: widest first keeps the long items at the front of the queue
+            perm = sorted(range(n), key=lambda i: -int(settings[i][0]))
+            arr = (_native.BeamSetting * n)(*[_native.BeamSetting(int(settings[i][0]), float(settings[i][1]), float(settings[i][2]),
+                                                                   float(settings[i][3])) for i in perm])
+            order = torch.argsort(ln, descending=True, stable=True).to(torch.int32) if (sort_by_length and B > 1) else None
+            wmax = max(int(s[0]) for s in settings)
+            ws = _workspace(dev, "beam", int(lib.ssd_ctc_beam_workspace_bytes(B * n, T, V, wmax)))
+            import ctypes
+
+            lib.check(lib.ssd_ctc_beam_grid(x.data_ptr(), B, T, V, sb, st, ln.data_ptr(),
+                                            order.data_ptr() if order is not None else None, int(blank), int(pad), int(space),
+                                            ctypes.cast(arr, ctypes.c_void_p), n, tok.data_ptr(), cnt.data_ptr(), score.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+            LAUNCHES["beam"] += 1
+            if perm != list(range(n)):
+                inv = torch.tensor([perm.index(i) for i in range(n)], device=dev)
+                tok, cnt, score = tok[inv], cnt[inv], score[inv]
+    return tok, cnt, score
+
+
+def row_logsumexp(x: torch.Tensor) -> torch.Tensor:
+    """(B,T,V) fp32 -> (B,T) fp32 log sum_v exp(x) on the device (``ssd_row_logsumexp``)."""
+    lib = _native.load()
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        x = _prep_log_probs(x, dev)
+        B, T, V = x.shape
+        out = torch.empty((B, T), dtype=torch.float32, device=dev)
+        if B and T:
+            sb, st = _strides(x)
+            lib.check(lib.ssd_row_logsumexp(x.data_ptr(), B, T, V, sb, st, out.data_ptr(), T, _stream_ptr(dev)))
+            LAUNCHES["aux"] += 1
+    return out
+
+
+def scale_if(x: torch.Tensor, g: torch.Tensor, expected: float) -> None:
+    """In place ``x *= g / expected`` decided ON THE DEVICE: when ``g == expected`` nothing is read or written.
+    ``x`` must cover its storage densely (any permutation of a contiguous tensor)."""
+    lib = _native.load()
+    dev = x.device
+    with torch.cuda.device(dev):
+        gd = g.detach().to(device=dev, dtype=torch.float32).reshape(1)
+        lib.check(lib.ssd_scale_if(x.data_ptr(), x.numel(), gd.data_ptr(), float(expected), _stream_ptr(dev)))
+        LAUNCHES["aux"] += 1
+
+
+_SCALARS: Dict[Tuple[int, float], torch.Tensor] = {}
+
+
+def device_scalar(dev: torch.device, value: float) -> torch.Tensor:
+    """A cached one-element fp32 device tensor (the kernels take multipliers by device pointer)."""
+    key = (_dev_index(dev), float(value))
+    t = _SCALARS.get(key)
+    if t is None:
+        if len(_SCALARS) > 256:
+            _SCALARS.clear()
+        t = torch.full((1,), float(value), dtype=torch.float32, device=dev)
+        _SCALARS[key] = t
+    return t
+
+
 def ctc_loss_fwd_bwd(
     log_probs_btv: torch.Tensor,
     input_lengths: torch.Tensor,
@@ -135,9 +231,12 @@ def ctc_loss_fwd_bwd(
     mean_denominator: int = 0,
     want_grad: bool = True,
     grad_mul: Optional[torch.Tensor] = None,
+    from_logits: bool = False,
 ):
     """One fused launch. log_probs_btv is indexed (b,t,v) with arbitrary b/t strides.
-    -> (nll fp32 (B,), grad with the strides of log_probs_btv or None)."""
+    -> (nll fp32 (B,), grad with the strides of log_probs_btv or None).
+    ``from_logits``: the input is the head's pre-softmax output (``ssd_ctc_loss_from_logits``); the gradient is then
+    the one with respect to the logits."""
     lib = _native.load()
     dev = _device(log_probs_btv)
     with torch.cuda.device(dev):
@@ -164,8 +263,9 @@ def ctc_loss_fwd_bwd(
         grad = torch.empty_strided(x.shape, x.stride(), dtype=torch.float32, device=dev) if want_grad else None
         if B:
             sb, st = _strides(x)
-            nbytes = int(lib.ssd_ctc_loss_workspace_bytes(B, T, V, S))
+            nbytes = int((lib.ssd_ctc_loss_from_logits_workspace_bytes if from_logits else lib.ssd_ctc_loss_workspace_bytes)(B, T, V, S))
             ws = _workspace(dev, "loss", nbytes)
+            _LAST_LOSS_WS[_dev_index(dev)] = ws
             # ragged batches with host-resident lengths (what the reference passes, losses.py:55): longest utterances
             # first, so that the CTAs that start last get the short ones.  Device-resident lengths are not inspected
             # (no sync, no extra launches on the training step).
@@ -176,7 +276,8 @@ def ctc_loss_fwd_bwd(
             gm = None
             if grad_mul is not None:
                 gm = grad_mul.detach().to(device=dev, dtype=torch.float32).reshape(1)
-            lib.check(lib.ssd_ctc_loss(x.data_ptr(), B, T, V, sb, st, tg.data_ptr() if S else None,
+            entry = lib.ssd_ctc_loss_from_logits if from_logits else lib.ssd_ctc_loss
+            lib.check(entry(x.data_ptr(), B, T, V, sb, st, tg.data_ptr() if S else None,
                                        tg.stride(0) if (S and B > 1) else max(S, 1), S, il.data_ptr(), tl.data_ptr(),
                                        order.data_ptr() if order is not None else None,
                                        int(blank), int(bool(zero_infinity)), int(mean_denominator),
@@ -186,6 +287,8 @@ def ctc_loss_fwd_bwd(
             # fp32 fast-path kernel + the fp64 kernel over whatever it flagged, or the fp64 kernel alone
             two = int(lib.ssd_ctc_loss_fallback_counter_offset(B, T, V, S)) != _NO_FAST
             LAUNCHES["loss"] += 2 if two else 1
+            if from_logits:
+                LAUNCHES["aux"] += 1
     return nll, grad
 
 
@@ -200,7 +303,7 @@ def loss_fallback_count(B: int, T: int, V: int, S: int, device=None) -> Optional
     if off == _NO_FAST:
         return None
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    ws = _WS.get((dev.index if dev.index is not None else torch.cuda.current_device(), "loss"))
+    ws = _LAST_LOSS_WS.get(_dev_index(dev))
     if ws is None or ws.numel() < off + 4:
         return None
     return int(ws[off:off + 4].view(torch.int32).item())

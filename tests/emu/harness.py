@@ -19,7 +19,7 @@ REPO = HERE.parent.parent
 CSRC = REPO / "silent-speech-decoder_b200" / "csrc"
 OUT = HERE / "_build"
 LIB = OUT / "libssd_ctc_emu.so"
-SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "capi.cu"]
+SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "aux.cu", "capi.cu"]
 
 
 def build(force: bool = False) -> Path:
@@ -81,8 +81,45 @@ def beam(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, width: 
     return [[int(x) for x in tok[b, : n[b]]] for b in range(B)], sc
 
 
+def beam_grid(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, settings, order=None):
+    """settings: list of (width, prune, bias, tmin). -> per setting (ids, scores), one launch for all."""
+    from silent_speech_decoder_b200._native import BeamSetting
+
+    lp = np.ascontiguousarray(lp, dtype=np.float32)
+    B, T, V = lp.shape
+    n = len(settings)
+    ln = np.asarray(lengths, dtype=np.int64)
+    tok = np.full((n, B, max(T, 1)), -7, dtype=np.int32)
+    cnt = np.full((n, B), -7, dtype=np.int32)
+    sc = np.full((n, B), np.nan, dtype=np.float64)
+    arr = (BeamSetting * max(n, 1))(*[BeamSetting(int(w), float(p), float(b), float(t)) for w, p, b, t in settings])
+    wmax = max([int(s[0]) for s in settings], default=1)
+    ws = np.zeros(lib.ssd_ctc_beam_workspace_bytes(B * max(n, 1), T, V, wmax) // 8 + 1, dtype=np.int64)
+    od = None if order is None else np.asarray(order, dtype=np.int32)
+    import ctypes as C
+
+    lib.check(lib.ssd_ctc_beam_grid(_ptr(lp), B, T, V, T * V, V, _ptr(ln), _ptr(od), blank, pad, space, C.cast(arr, C.c_void_p), n,
+                                    _ptr(tok), _ptr(cnt), _ptr(sc), _ptr(ws), ws.nbytes, None))
+    return [([[int(x) for x in tok[i, b, : cnt[i, b]]] for b in range(B)], sc[i]) for i in range(n)]
+
+
+def row_lse(lib, x: np.ndarray):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, T, V = x.shape
+    out = np.full((B, T), np.nan, dtype=np.float32)
+    lib.check(lib.ssd_row_logsumexp(_ptr(x), B, T, V, T * V, V, _ptr(out), T, None))
+    return out
+
+
+def scale_if(lib, x: np.ndarray, g: float, expected: float):
+    x = np.ascontiguousarray(x, dtype=np.float32).copy()
+    gv = np.asarray([g], dtype=np.float32)
+    lib.check(lib.ssd_scale_if(_ptr(x), x.size, _ptr(gv), float(expected), None))
+    return x
+
+
 def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity: bool = True, mean_den: int = 0,
-         want_grad: bool = True, grad_mul=None, with_fallbacks: bool = False):
+         want_grad: bool = True, grad_mul=None, with_fallbacks: bool = False, from_logits: bool = False):
     lp = np.ascontiguousarray(lp, dtype=np.float32)
     B, T, V = lp.shape
     il = np.asarray(in_len, dtype=np.int64)
@@ -91,10 +128,11 @@ def loss(lib, lp: np.ndarray, in_len, targets, tg_len, blank: int, zero_infinity
     S = tg.shape[1]
     nll = np.full((B,), np.nan, dtype=np.float32)
     grad = np.full_like(lp, np.nan) if want_grad else None
-    nbytes = lib.ssd_ctc_loss_workspace_bytes(B, T, V, S)
+    nbytes = (lib.ssd_ctc_loss_from_logits_workspace_bytes if from_logits else lib.ssd_ctc_loss_workspace_bytes)(B, T, V, S)
     ws = np.zeros(nbytes // 8 + 1, dtype=np.int64)
     gm = None if grad_mul is None else np.asarray([grad_mul], dtype=np.float32)
-    lib.check(lib.ssd_ctc_loss(_ptr(lp), B, T, V, T * V, V, _ptr(tg), S, S, _ptr(il), _ptr(tl), None, blank, int(zero_infinity),
+    entry = lib.ssd_ctc_loss_from_logits if from_logits else lib.ssd_ctc_loss
+    lib.check(entry(_ptr(lp), B, T, V, T * V, V, _ptr(tg), S, S, _ptr(il), _ptr(tl), None, blank, int(zero_infinity),
                                mean_den, _ptr(gm), _ptr(nll), _ptr(grad), _ptr(ws), ws.nbytes, None))
     if with_fallbacks:  # utterances that took the exact fp64 path (None: the fast path does not cover the shape)
         off = lib.ssd_ctc_loss_fallback_counter_offset(B, T, V, S)

@@ -159,3 +159,102 @@ def test_beam_random_configurations():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(repo, "profiles", "fuzz_beam.py"), "30", "7"], capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ round 2: config 4, decoder grid, logits, sharding
+@pytest.mark.parametrize("kind", ["peaked", "flat"])
+@pytest.mark.parametrize("width", [1, 10, 50, 200])
+def test_beam_t4000_widths(golden_dir, kind, width):
+    """BASELINE.json config 4: T=4000, widths 1/10/50/200.  Expected transcripts and scores were produced by
+    oracle/beam.py (oracle/make_beam_golden_long.py; minutes of CPU, hence frozen); inputs regenerate from the seed."""
+    from oracle.make_beam_golden_long import LENGTHS, inputs
+
+    z = np.load(os.path.join(golden_dir, "beam_t4000.npz"))
+    lp = torch.from_numpy(inputs(kind))
+    text, score = _native(lp, torch.tensor(LENGTHS), width)
+    assert text == list(z[f"{kind}_w{width}.text"])
+    assert np.abs(score - z[f"{kind}_w{width}.score"]).max() <= SCORE_ATOL
+
+
+def test_beam_upstream(golden_dir):
+    """Against the REAL pyctcdecode (tests/golden/beam_upstream.npz from oracle/make_beam_golden_upstream.py).
+    The file cannot be produced in this image (library not installable): skipped, beam parity UNPINNED, until it exists."""
+    path = os.path.join(golden_dir, "beam_upstream.npz")
+    if not os.path.exists(path):
+        pytest.skip("beam_upstream.npz not generated yet (needs pyctcdecode): beam parity unpinned")
+    from oracle.make_beam_golden_upstream import CASES, case_inputs
+
+    z = np.load(path)
+    for name, gen, B, T, seed, width, prune, bias in CASES:
+        lp, ln = case_inputs(gen, B, T, seed)
+        text, score = _native(torch.from_numpy(lp), torch.tensor(ln), width, prune, bias)
+        assert text == list(z[f"{name}.text"]), name
+        assert np.abs(score - z[f"{name}.score"]).max() <= SCORE_ATOL, name
+
+
+def test_beam_grid_single_launch_vs_oracle():
+    """Scope row f-3: the reference's FULL_DECODERS_SILENT beam points (config_builder.py:86-93, LM point aside) plus
+    a width-1 and a width-200 point, one launch, each setting against oracle/beam.py."""
+    _, space = ctc._beam_label_strings(V)
+    B, T = 12, 260
+    lp = torch.cat([synth.peaked(B // 2, T, 41), synth.flat(B // 2, T, 42)])
+    ln = synth.ragged_lengths(B, T, 43)
+    ln[0], ln[-1] = T, 0
+    settings = [(20, -10.0, 0.2, -5.0), (50, -12.0, 0.1, -5.0), (100, -12.0, 0.05, -5.0), (1, -10.0, 0.0, -5.0), (200, -10.0, 0.0, -5.0)]
+    n0 = ops.LAUNCHES["beam"]
+    tok, cnt, score = ops.beam_grid_ids(lp, ln, V.blank_id, V.pad_id, space, settings)
+    assert ops.LAUNCHES["beam"] == n0 + 1
+    text_of, _ = ctc._beam_label_strings(V)
+    for i, (w, p, b, _) in enumerate(settings):
+        got = ctc._rows_to_strings(tok[i], cnt[i], text_of, normalise_space=True)
+        want = _oracle(lp.numpy(), ln.tolist(), w, p, b)
+        assert got == [t for t, _ in want], (w, p, b)
+        assert np.abs(score[i].cpu().numpy() - np.array([s for _, s in want])).max() <= SCORE_ATOL
+        # and bit-identical to a launch of its own
+        t1, c1, s1 = ops.beam_ids(lp, ln, V.blank_id, V.pad_id, space, w, p, b)
+        assert torch.equal(c1, cnt[i]) and torch.equal(s1, score[i])
+        assert all(torch.equal(t1[r, : c1[r]], tok[i, r, : c1[r]]) for r in range(B))
+
+
+def test_decoders_accept_logits():
+    """Scope row f-2, decoder side: greedy's argmax and the beam search's own log-softmax are invariant to the
+    per-frame constant log_softmax removes, so the head's pre-softmax output can be handed over as it is."""
+    g = torch.Generator().manual_seed(3)
+    B, T = 6, 400
+    lp = torch.cat([synth.peaked(3, T, 51), synth.flat(3, T, 52)])
+    logits = lp + 4.0 * torch.randn(B, T, 1, generator=g)
+    ln = synth.ragged_lengths(B, T, 53)
+    for bias in (0.0, 0.3):
+        assert ctc._greedy_decode(logits, ln, V.blank_id, bias) == og.greedy_ids(lp.numpy(), ln.tolist(), V.blank_id, bias)
+        want = _oracle(lp.numpy(), ln.tolist(), 50, -10.0, bias)
+        text, score = _native(logits, ln, 50, -10.0, bias)
+        assert text == [t for t, _ in want]
+        assert np.abs(score - np.array([s for _, s in want])).max() <= SCORE_ATOL
+
+
+def test_greedy_bias_over_many_tiles():
+    # blank bias with more than two 128-frame tiles per utterance: the bias is applied to the compared value, the
+    # TMA tile is never written (the earlier in-place add was a cross-proxy hazard once a buffer was re-filled)
+    lp = synth.flat(5, 1000, 61)
+    ln = torch.tensor([1000, 999, 640, 257, 128])
+    for bias in (1.5, -0.7):
+        assert ctc._greedy_decode(lp.cuda(), ln, V.blank_id, bias) == og.greedy_ids(lp.numpy(), ln.tolist(), V.blank_id, bias)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_decode_equals_single_rank(world):
+    """dist.shard_by_cost + per-rank decode + reassembly == one decode of the whole set (what config 5 does with one
+    process per GPU; here the ranks' shares are decoded one after the other on this GPU)."""
+    from silent_speech_decoder_b200 import dist as sdist
+
+    B, T = 96, 300
+    lp = synth.peaked(B, T, 71)
+    ln = synth.ragged_lengths(B, T, 72)
+    dec = ctc.build_decoder("beam", V, beam_width=50)
+    whole = dec(lp, ln)
+    out = [None] * B
+    for mine in sdist.shard_by_cost(ln.tolist(), world):
+        sel = torch.tensor(mine)
+        for i, t in zip(mine, dec(lp[sel], ln[sel])):
+            out[i] = t
+    assert out == whole

@@ -8,7 +8,9 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import beam as ob
 from oracle import edit as oe
+from oracle import greedy as og
 from silent_speech_decoder_b200 import ops, synth
 from silent_speech_decoder_b200.data.vocab import Vocab
 from silent_speech_decoder_b200.decoding import ctc
@@ -116,10 +118,14 @@ def test_decoder_grid_matches_single_runs(tmp_path):
     lp = synth.peaked(12, 250, 4400)  # host tensors, as the reference's loop holds them
     ln = synth.ragged_lengths(12, 250, 4401)
     refs = [t if t.strip() else "x" for t in ctc.build_decoder("greedy", V)(synth.peaked(12, 250, 4402), ln)]
+    n0 = ops.LAUNCHES["beam"]
     got = g.add(range(12), refs, lp, ln)
-    assert got["greedy"] == ctc.build_decoder("greedy", V)(lp, ln)
+    assert ops.LAUNCHES["beam"] == n0 + 1  # the three beam settings shared ONE launch
+    # every setting against the CPU oracle (greedy: pinned to the reference; beam: the restatement)
+    assert got["greedy"] == og.greedy_text(lp.numpy(), ln.tolist(), V.tokens, V.blank_id, V.pad_id)
+    for name, (w, p, b) in {"beam20_bias": (20, -10.0, 0.2), "beam50": (50, -12.0, 0.1), "beam100": (100, -12.0, 0.05)}.items():
+        assert got[name] == ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, w, p, b)(lp.numpy(), ln.tolist()), name
     assert got["beam20_bias"] == ctc.build_decoder("beam", V, beam_width=20, beam_prune_logp=-10.0, blank_bias=0.2)(lp, ln)
-    assert got["beam100"] == ctc.build_decoder("beam", V, beam_width=100, beam_prune_logp=-12.0, blank_bias=0.05)(lp, ln)
     m = g.finish(tmp_path)
     assert set(m) == {"greedy", "beam20_bias", "beam50", "beam100"}
     assert m["beam50"]["decoder"] == {"type": "beam", "beam_width": 50, "alpha": 0.5, "beta": 0.0, "beam_prune_logp": -12.0,

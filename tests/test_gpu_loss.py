@@ -225,3 +225,126 @@ def test_random_shapes_against_exact_kernel():
     r = subprocess.run([sys.executable, os.path.join(repo, "profiles", "fuzz_loss.py"), "40", "5"], capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "all 40 cases ok" in r.stdout
+
+
+@pytest.mark.timeout(300)
+def test_full_size_cfg2_gradient_against_fp64_oracle():
+    """Config 2 at FULL size (B=256, T=1000, S~U[50,200]): nll and the whole (B,T,V) gradient against the reference's
+    ATen op evaluated in fp64 on the host (oracle.ctc_loss.torch_ctc), to the north_star tolerance."""
+    B, T, S = 256, 1000, 200
+    lp = synth.flat(B, T, 1002)
+    tg, tl = synth.targets(B, S, 1002)
+    il = torch.full((B,), T)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    nll64, mean64, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    x = lp.cuda().requires_grad_(True)
+    out = DistillationCTCLoss(48, 1, LossWeights(0.0, 1.0))(x, il, tg.cuda(), tl.cuda(), x, None)
+    out["total"].backward()
+    assert abs(out["ctc"].item() - float(mean64)) <= RTOL * float(mean64)
+    err = (x.grad.cpu().double() - g64).abs().amax(dim=(1, 2))
+    ref = g64.abs().amax(dim=(1, 2))
+    assert (err <= RTOL * ref).all(), (err / ref).max().item()   # per utterance, not only over the batch
+    assert ops.loss_fallback_count(B, T, 48, S) == 0
+
+
+@pytest.mark.parametrize("name", ["same_res", "resampled", "resampled_nolen", "normalised"])
+def test_module_with_teacher_matches_reference(golden_dir, name):
+    """total / ctc / distill and both gradients of the reference's DistillationCTCLoss run WITH a teacher
+    (tests/golden/distill_ref.npz).  lambda_ctc != 1 also exercises the up-front gradient scale (expect_grad)."""
+    z = np.load(os.path.join(golden_dir, "distill_ref.npz"))
+    c = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(name + ".")}
+    fn = DistillationCTCLoss(48, 1, LossWeights(*c["lam"].tolist()), normalize_distill=bool(c["norm"]))
+    x = torch.from_numpy(c["lp"]).cuda().requires_grad_(True)
+    s = torch.from_numpy(c["student"]).cuda().requires_grad_(True)
+    t_len = torch.from_numpy(c["teacher_len"]).cuda() if c["teacher_len"].size else None
+    out = fn(x, torch.from_numpy(c["il"]).cuda(), torch.from_numpy(c["tg"]).cuda(), torch.from_numpy(c["tl"]).cuda(), s,
+             torch.from_numpy(c["teacher"]).cuda(), t_len)
+    out["total"].backward()
+    for k in ("total", "ctc", "distill"):
+        np.testing.assert_allclose(out[k].item(), c[k], rtol=2e-6, err_msg=k)
+    np.testing.assert_allclose(s.grad.cpu().numpy(), c["grad_student"], rtol=1e-5, atol=1e-9)
+    g = c["grad_lp"]
+    assert np.abs(x.grad.cpu().numpy() - g).max() <= 2e-5 * np.abs(g).max()   # the reference's fp32 gradient is the looser side
+
+
+def test_unexpected_upstream_gradient_is_applied():
+    """The kernel pre-scales by the scalar it expects from autograd; a different one must still give the right
+    gradient (ssd_scale_if's slow branch), also when backward runs twice through the same graph."""
+    B, T = 4, 50
+    lp = synth.flat(B, T, 31)
+    tg, tl = synth.targets(B, 8, 32)
+    il = torch.tensor([50, 41, 50, 33])
+    _, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    x = lp.cuda().requires_grad_(True)
+    fn = DistillationCTCLoss(48, 1, LossWeights(0.0, 0.65))
+    out = fn(x, il, tg.cuda(), tl.cuda(), x, None)
+    (3.0 * out["total"]).backward(retain_graph=True)          # upstream 3 * 0.65, the kernel expected 0.65
+    assert (x.grad.cpu().double() - 1.95 * g64).abs().max() <= 2 * RTOL * 1.95 * g64.abs().max()
+    x.grad = None
+    out["ctc"].backward()                                       # second pass, upstream 1.0
+    assert (x.grad.cpu().double() - g64).abs().max() <= 2 * RTOL * g64.abs().max()
+    # reductions 'sum' and 'none' through the functional form
+    for red in ("sum", "none"):
+        y = lp.cuda().transpose(0, 1).detach().requires_grad_(True)
+        v = ctc_loss(y, tg.cuda(), il, tl, blank=1, reduction=red, zero_infinity=True)
+        w = torch.tensor([1.0, 2.0, 0.5, 3.0], device="cuda")
+        (v * w).sum().backward() if red == "none" else v.backward()
+        y64 = lp.double().transpose(0, 1).detach().requires_grad_(True)
+        r = torch.nn.functional.ctc_loss(y64, tg, il, tl, blank=1, reduction=red, zero_infinity=True)
+        (r * w.cpu().double()).sum().backward() if red == "none" else r.backward()
+        assert (y.grad.cpu().double() - y64.grad).abs().max() <= 2 * RTOL * y64.grad.abs().max(), red
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_loss_from_logits(golden_dir, exact, monkeypatch):
+    """Scope row f-2 on the reference's own head output: cfg1's fixture holds CTCHead log-probs of the random-init
+    mps_fast_basic encoder; logits = those log-probs plus an arbitrary per-frame constant (what log_softmax removes).
+    Loss and d/d(logits) against head + reference loss in fp64."""
+    if exact:
+        monkeypatch.setenv("SSD_LOSS_EXACT", "1")
+    z = np.load(os.path.join(golden_dir, "cfg1_ref.npz"))
+    lp, il, tg, tl = (torch.from_numpy(z[k]) for k in ("lp", "il", "tg", "tl"))
+    g = torch.Generator().manual_seed(5)
+    logits = lp + 7.0 * torch.randn(lp.shape[0], lp.shape[1], 1, generator=g)
+    x64 = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(x64, -1).transpose(0, 1), tg, il, tl, blank=1, reduction="mean", zero_infinity=True)
+    ref.backward()
+    x = logits.cuda().requires_grad_(True)
+    out = DistillationCTCLoss(48, 1, LossWeights(0.0, 1.0), from_logits=True)(x, il, tg.cuda(), tl.cuda(), x, None)
+    out["total"].backward()
+    assert abs(out["ctc"].item() - ref.item()) <= RTOL * ref.item()
+    assert (x.grad.cpu().double() - x64.grad).abs().max() <= RTOL * x64.grad.abs().max()
+    np.testing.assert_allclose(ops.row_logsumexp(logits.cuda()).cpu().numpy(), torch.logsumexp(logits.double(), -1).numpy(), atol=2e-6, rtol=0)
+    # and at config-2 size the logits entry and the log-prob entry agree with each other
+    if not exact:
+        B, T, S = 256, 1000, 200
+        big = torch.randn(B, T, 48, generator=g).cuda()
+        tg2, tl2 = synth.targets(B, S, 1002)
+        il2 = torch.full((B,), T)
+        n1, g1 = ops.ctc_loss_fwd_bwd(big, il2, tg2, tl2, blank=1, from_logits=True)
+        n2, g2 = ops.ctc_loss_fwd_bwd(torch.log_softmax(big, -1), il2, tg2, tl2, blank=1)
+        assert ((n1 - n2).abs() / n2.abs()).max().item() < 2e-6
+        assert (g1 - g2).abs().max().item() <= RTOL * g2.abs().max().item()
+
+
+def test_two_streams_do_not_share_scratch():
+    """Per-(device, stream) workspaces: interleaved launches on two streams give the single-stream results."""
+    B, T, S = 64, 300, 40
+    a, b = synth.flat(B, T, 91).cuda(), synth.flat(B, T, 92).cuda()
+    tg, tl = synth.targets(B, S, 93)
+    il = torch.full((B,), T)
+    ra, rb = ops.ctc_loss_fwd_bwd(a, il, tg, tl, blank=1), ops.ctc_loss_fwd_bwd(b, il, tg, tl, blank=1)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    tgd, tld, ild = tg.cuda(), tl.cuda(), il.cuda()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            o1 = ops.ctc_loss_fwd_bwd(a, ild, tgd, tld, blank=1)
+        with torch.cuda.stream(s2):
+            o2 = ops.ctc_loss_fwd_bwd(b, ild, tgd, tld, blank=1)
+        outs.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in outs:
+        assert torch.equal(o1[0], ra[0]) and torch.equal(o1[1], ra[1])
+        assert torch.equal(o2[0], rb[0]) and torch.equal(o2[1], rb[1])

@@ -57,3 +57,21 @@ def test_empty_and_unk():
     lp[0, :, v.unk_id] = 0.0
     assert dec(lp, [0]) == [""]
     assert dec(lp, [4]) == [ob.UNK_GLYPH]
+
+
+def test_restatement_matches_upstream(golden_dir):
+    """Consumes tests/golden/beam_upstream.npz -- outputs of the REAL pyctcdecode called as the reference calls
+    it, written by oracle/make_beam_golden_upstream.py on a machine that has the library.  Absent here (no
+    network, library not installable): beam parity stays UNPINNED until the file is committed."""
+    path = os.path.join(golden_dir, "beam_upstream.npz")
+    if not os.path.exists(path):
+        pytest.skip("beam_upstream.npz not generated yet (needs pyctcdecode): beam parity unpinned")
+    from oracle.make_beam_golden_upstream import CASES, case_inputs
+
+    z = np.load(path)
+    v = Vocab.default()
+    for name, gen, B, T, seed, width, prune, bias in CASES:
+        lp, ln = case_inputs(gen, B, T, seed)
+        out = ob.BeamDecoder(v.tokens, v.blank_id, v.pad_id, width, prune, bias).decode_with_scores(lp, ln)
+        assert [t for t, _ in out] == list(z[f"{name}.text"]), name
+        np.testing.assert_allclose([s for _, s in out], z[f"{name}.score"], rtol=0, atol=1e-4, err_msg=name)
