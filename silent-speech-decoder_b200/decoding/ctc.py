@@ -101,6 +101,43 @@ def _rows_to_strings(tok: torch.Tensor, cnt: torch.Tensor, text: Sequence[str], 
     return out
 
 
+# Host-resident batches above this size are decoded in chunks on two alternating streams: chunk k+1's H2D copy and
+# kernel run while chunk k's ids come back and its strings are assembled on the host (the reference hands its
+# decoders CPU tensors, evaluate.py:299; at config 3 that is a 960 MB copy and ~20 ms of string work per call).
+PIPELINE_MIN_BYTES = 96 << 20
+PIPELINE_CHUNK = 1776  # utterances: twelve per SM, about two waves of resident beam CTAs
+
+
+def _pipelined(log_probs: torch.Tensor, lengths: torch.Tensor, launch, to_strings) -> List[str]:
+    """``launch(x_dev, len_dev) -> tensors``; ``to_strings(*tensors) -> List[str]`` (does the D2H copies)."""
+    B = log_probs.size(0)
+    big = (not log_probs.is_cuda) and log_probs.dim() == 3 and log_probs.numel() * 4 >= PIPELINE_MIN_BYTES and B >= 2 * PIPELINE_CHUNK
+    if not big:
+        return to_strings(*launch(log_probs, lengths))
+    dev = ops._device(log_probs)
+    ln = torch.as_tensor(lengths)
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream(dev))
+    out: List[str] = []
+    pending = None
+    for k, lo in enumerate(range(0, B, PIPELINE_CHUNK)):
+        hi = min(B, lo + PIPELINE_CHUNK)
+        s = streams[k & 1]
+        with torch.cuda.stream(s):
+            x = log_probs[lo:hi].to(dev, non_blocking=True)
+            res = launch(x, ln[lo:hi])
+        if pending is not None:
+            with torch.cuda.stream(pending[0]):
+                out.extend(to_strings(*pending[1]))  # blocks on the OTHER stream only
+        pending = (s, res)
+    with torch.cuda.stream(pending[0]):
+        out.extend(to_strings(*pending[1]))
+    for s in streams:
+        torch.cuda.current_stream(dev).wait_stream(s)
+    return out
+
+
 def _greedy_decode(log_probs: torch.Tensor, lengths: torch.Tensor, blank_id: int, blank_bias: float = 0.0) -> List[List[int]]:
     """Argmax per frame, collapse repeats/blanks (reference ctc.py:16-36). Returns id lists."""
     tok, cnt = ops.greedy_ids(log_probs, lengths, blank=blank_id, blank_bias=blank_bias)
@@ -112,8 +149,9 @@ def build_greedy_decoder(vocab: Vocab, blank_bias: float = 0.0) -> DecoderFn:
     greedy_text = ["" if i in (vocab.blank_id, vocab.pad_id) else vocab.tokens[i] for i in range(vocab.size)]
 
     def decode(log_probs: torch.Tensor, lengths: torch.Tensor) -> List[str]:
-        tok, cnt = ops.greedy_ids(log_probs, lengths, blank=vocab.blank_id, blank_bias=blank_bias)
-        return _rows_to_strings(tok, cnt, greedy_text, normalise_space=False)
+        return _pipelined(log_probs, lengths,
+                          lambda x, n: ops.greedy_ids(x, n, blank=vocab.blank_id, blank_bias=blank_bias),
+                          lambda tok, cnt: _rows_to_strings(tok, cnt, greedy_text, normalise_space=False))
 
     return decode
 
@@ -161,11 +199,10 @@ def build_beam_decoder(
             raise ValueError(
                 f"Input logits shape is {tuple(log_probs.shape[1:])}, but vocabulary is size {vocab.size}"
             )
-        tok, cnt, _ = ops.beam_ids(
-            log_probs, lengths, blank=vocab.blank_id, pad=pad, space=space, beam_width=beam_width,
-            beam_prune_logp=beam_prune_logp, blank_bias=blank_bias,
-        )
-        return _rows_to_strings(tok, cnt, text, normalise_space=True)
+        return _pipelined(log_probs, lengths,
+                          lambda x, n: ops.beam_ids(x, n, blank=vocab.blank_id, pad=pad, space=space, beam_width=beam_width,
+                                                    beam_prune_logp=beam_prune_logp, blank_bias=blank_bias)[:2],
+                          lambda tok, cnt: _rows_to_strings(tok, cnt, text, normalise_space=True))
 
     return decode
 
