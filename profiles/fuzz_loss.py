@@ -24,9 +24,14 @@ for c in range(cases):
     B = int(rng.choice([1, 2, 3, 7, 33, 150, 297, 600, 900]))
     T = int(rng.choice([1, 5, 8, 9, 40, 97, 160, 200, 333, 600]))
     S = int(min(rng.choice([1, 2, 10, 40, 63, 64, 100, 127, 128, 200, 255]), max(1, T)))
-    kind = rng.choice(["flat", "peaked", "mild"])
-    lp = synth.flat(B, T, 7000 + c) if kind == "flat" else synth.peaked(B, T, 7000 + c, boost=8.0 if kind == "peaked" else 2.0)
-    tg, tl = synth.targets(B, S, 8000 + c, s_min=1)
+    kind = rng.choice(["flat", "peaked", "mild", "trained"])
+    if kind == "trained" and T >= 8:  # confident posteriors on the utterances' own transcripts
+        lp, tg, tl = synth.peaked_aligned(B, T, 7000 + c, n_labels=(1, max(1, min(S, T // 2))))
+        if tg.size(1) < S:
+            tg = torch.nn.functional.pad(tg, (0, S - tg.size(1)))
+    else:
+        lp = synth.flat(B, T, 7000 + c) if kind == "flat" else synth.peaked(B, T, 7000 + c, boost=8.0 if kind == "peaked" else 2.0)
+        tg, tl = synth.targets(B, S, 8000 + c, s_min=1)
     il = synth.ragged_lengths(B, T, 9000 + c)
     if B > 2:
         il[1] = 0
@@ -35,6 +40,8 @@ for c in range(cases):
     env = {"SSD_LOSS_GRID": str(grid)} if grid else {}
     if rng.random() < 0.3:
         env["SSD_LOSS_NOLATE"] = "1"
+    if rng.random() < 0.5:
+        env["SSD_LOSS_MULTI"] = str(int(rng.integers(0, 2)))  # one kernel per strip width / one launch-wide width
     os.environ.update(env)
     tag = f"case {c}: B={B} T={T} S={S} {kind} {env}"
     try:

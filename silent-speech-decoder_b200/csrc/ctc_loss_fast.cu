@@ -94,6 +94,17 @@ constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
 constexpr int F_FR = SSD_F_FR;  // frames interleaved in the gradient stage
 constexpr int F_TOP = 40;  // renormalised strips have their largest cell in [2^40, 2^41)
 constexpr int F_SPAD = 256;  // label staging capacity (S <= 255 on this path)
+// Strip widths compiled in, one kernel each.  An utterance runs at the smallest one that holds its 2S+1 cells: sweeps,
+// block rows and products all scale with it (config 2: labels U[50,200] need 4..13 cells per lane, 9 on average; one
+// launch-wide width made every utterance pay for the longest).
+constexpr int F_NCLS = 7;
+__host__ __device__ inline int fast_class_of(int cells_per_lane) {
+  return cells_per_lane <= 4 ? 0 : cells_per_lane <= 6 ? 1 : cells_per_lane <= 8 ? 2 : cells_per_lane <= 10 ? 3
+       : cells_per_lane <= 12 ? 4 : cells_per_lane <= 14 ? 5 : 6;
+}
+__host__ __device__ inline int fast_width_of(int cls) { return 4 + 2 * cls; }
+constexpr unsigned F_YIELD_NS = 3000u;  // head start given to CTAs on idle SMs at the first draw of a kernel
+constexpr int F_RANK_MAX = 1024;  // batches up to this size are ranked by cost within their class (one CTA, O(B^2 / 1024))
 #ifndef SSD_F_REBASE
 #define SSD_F_REBASE 32
 #endif
@@ -162,8 +173,15 @@ struct FastParams {
   const float* grad_mul;
   float* nll;
   float* grad;
-  unsigned* counter;   // [0] utterance queue, [1] number of flagged utterances
-  unsigned* sm_slot;   // [#SM] arrival counter of CTAs per SM (role rotation, see loss_fast_kernel)
+  unsigned* counter;   // [1] number of flagged utterances, [2] checkpoint regions handed out, [16 + 4c ..] class c: draws, head, tail
+  unsigned* sm_slot;   // [#SM] arrival counter of working CTAs per SM (role rotation, dealing); [512 + 2 smid + s] region s of SM busy
+  // written by loss_fast_prepass_kernel: utterances grouped by strip-width class (widest first), by decreasing cost within
+  const int* cls_list;   // [B]
+  const int* cls_start;  // [F_NCLS] first position of class c in cls_list
+  const int* cls_count;  // [F_NCLS]
+  int ranked;            // cls_list is cost-ordered within a class: the second CTA of an SM draws from the cheap end
+  int region_by_sm;      // 1: more utterances than checkpoint regions, a CTA takes one of its SM's two regions and returns it
+  int pdl_wait;          // first class kernel after the prepass: wait for it (programmatic dependent launch)
   int* flags;          // [B] non-zero = recompute on the exact path (1 not covered, 2 D1, 4 D2, 8 D3, 16 D4)
   unsigned char* ckpt; // per CTA: [2 dirs][nb_max] records
   size_t ckpt_cta_bytes, ckpt_rec_bytes;
@@ -226,6 +244,8 @@ struct FastScal {
   float inv_zm;    // 1 / mantissa of Z
   int ez;          // exponent of Z
   int rot;         // role rotation of this CTA (0/1)
+  int second;      // this CTA was the second working one to arrive on its SM
+  int region;      // checkpoint region of this CTA
 };
 
 // ------------------------------------------------------------------ strips
@@ -1092,11 +1112,126 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
 }
 
 // ------------------------------------------------------------------ kernel
+// ------------------------------------------------------------------ prepass: utterances -> strip-width classes
+struct PrepassParams {
+  const int64_t* in_len;
+  const int64_t* tg_len;
+  int B;
+  int64_t T;
+  int S_max, nc_max, nc_min;
+  int rank;  // 1: order every class by decreasing cost (B <= F_RANK_MAX)
+  int* list;
+  int* start;
+  int* count;
+};
+
+// class (0..F_NCLS-1) and cost of utterance j.  Rows the fast path does not take (bad lengths, no frames, a lattice wider
+// than the launch holds) ride in the widest class at cost 0: the kernel there flags them for the exact path unseen.
+__device__ __forceinline__ int prepass_class(const PrepassParams& P, int j, int& cost) {
+  const int64_t tl = P.in_len[j], sl = P.tg_len[j];
+  const bool bad = tl < 0 || tl > P.T || sl < 0 || sl > P.S_max || tl == 0 || 2 * sl + 1 > 32 * (int64_t)P.nc_max;
+  int need = bad ? P.nc_max : (int)((2 * sl + 1 + 31) / 32);
+  need = need < P.nc_min ? P.nc_min : need;
+  cost = bad ? 0 : (int)tl;
+  return fast_class_of(need);
+}
+
+__global__ void __launch_bounds__(1024) loss_fast_prepass_kernel(const PrepassParams P) {
+  __shared__ int cnt[F_NCLS], first[F_NCLS], fill[F_NCLS];
+  __shared__ unsigned long long key[F_RANK_MAX];
+  const int tid = (int)threadIdx.x;
+  if (tid < F_NCLS) cnt[tid] = fill[tid] = 0;
+  __syncthreads();
+  for (int j = tid; j < P.B; j += 1024) {
+    int cost;
+    const int c = prepass_class(P, j, cost);
+    atomicAdd(&cnt[c], 1);
+    if (P.rank) key[j] = ((unsigned long long)c << 40) | (unsigned long long)(unsigned)cost;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int o = 0;
+    for (int c = F_NCLS - 1; c >= 0; --c) {  // widest class first
+      first[c] = o;
+      P.start[c] = o;
+      P.count[c] = cnt[c];
+      o += cnt[c];
+    }
+  }
+  __syncthreads();
+  if (P.rank) {
+    // (class, cost) descending, index ascending: the rank IS the position in the list
+    for (int j = tid; j < P.B; j += 1024) {
+      const unsigned long long mine = key[j];
+      int rk = 0;
+      for (int i = 0; i < P.B; ++i) {
+        const unsigned long long o = key[i];
+        rk += (o > mine || (o == mine && i < j)) ? 1 : 0;
+      }
+      P.list[rk] = j;
+    }
+  } else {
+    for (int j = tid; j < P.B; j += 1024) {
+      int cost;
+      const int c = prepass_class(P, j, cost);
+      P.list[first[c] + atomicAdd(&fill[c], 1)] = j;  // any order within the class: results do not depend on it
+    }
+  }
+}
+
+// ------------------------------------------------------------------ kernel (one per strip width)
 template <int NC>
 __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParams P) {
   SSD_DYN_SMEM(smem);
-  const FastSmem M = fast_smem_layout(P.V, P.RS, P.S_max + 4, P.nb_max);
+  constexpr int CLS = (NC - 4) / 2;
+  static_assert(NC >= 4 && NC <= 16 && NC % 2 == 0, "strip widths 4, 6, .., 16");
+  // The kernels of one call are launched back to back with programmatic stream serialisation: each lets its
+  // successor start at once (they are independent), so all widths run side by side out of ONE stream.  Only the first
+  // one waits for the prepass; its successors cannot start before every one of its CTAs has passed that wait.
+#ifndef SSD_EMU
+  if (P.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  const int n_cls = P.cls_count[CLS];
+  const int* my_list = P.cls_list + P.cls_start[CLS];
+  unsigned* my_ctr = P.counter + 16 + 4 * CLS;
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Who works is decided by the FIRST DRAW, not by the block index: every width's kernel has as many CTAs as there are
+  // slots, the block scheduler hands them out from SM 0 upwards, and with "block index < utterances of this width"
+  // all widths piled their work onto the same few SMs.  A CTA that finds a working CTA already on its SM lets the
+  // CTAs on idle SMs draw first; whoever draws nothing leaves before touching shared memory.
+  // my_ctr[0] counts draws (at most n_cls succeed); [1] / [2] are the two ends of the class list (cost-ordered when
+  // ranked: the first CTA of an SM draws from the expensive end, a second one from the cheap end, later draws always
+  // from the expensive end).  heads + tails <= n_cls, so the ends never cross.
+  __shared__ int first_draw[4];  // utterance position, SM id, working CTAs found on the SM
+  if (tid == 0) {
+#ifdef SSD_EMU
+    const unsigned smid = 0u, here = blockIdx.x & 1u;
+#else
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned here = *reinterpret_cast<volatile unsigned*>(P.sm_slot + smid);
+    if (here > 0u) {
+      // a working CTA of the SAME width here: sharing its code in the instruction cache is worth more than an idle SM
+      // is to a narrower width; of another width: everybody else first
+      const unsigned other = *reinterpret_cast<volatile unsigned*>(P.sm_slot + 256 + smid);
+      __nanosleep(other == (unsigned)CLS + 1u ? F_YIELD_NS / 4 : 2 * F_YIELD_NS);
+    }
+#endif
+    int u = n_cls > 0 ? (int)atomicAdd(my_ctr, 1u) : 0;
+    if (u < n_cls) {
+      const bool tail = P.ranked && here > 0u;
+      const int k = (int)atomicAdd(my_ctr + (tail ? 2 : 1), 1u);
+      u = tail ? n_cls - 1 - k : k;
+    } else {
+      u = -1;
+    }
+    first_draw[0] = u;
+    first_draw[1] = (int)smid;
+  }
+  __syncthreads();
+  if (first_draw[0] < 0) return;  // more CTAs than this width has utterances
+  const FastSmem M = fast_smem_layout(P.V, P.RS, P.S_max + 4, P.nb_max);
 
   int* lab = reinterpret_cast<int*>(smem + M.lab_off);
   int* pos = reinterpret_cast<int*>(smem + M.pos_off);
@@ -1140,22 +1275,41 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
   FastScal* sc = reinterpret_cast<FastScal*>(smem + *reinterpret_cast<volatile unsigned*>(&pin_scal));
 #endif
 
-  unsigned char* ckpt_cta = P.ckpt + (size_t)blockIdx.x * P.ckpt_cta_bytes;
   unsigned qbase = 0u, uiter = 0u, nraw = 0u;
   // Warp w issues from sub-partition w % 4.  Two CTAs share an SM; the second one to arrive uses a mirrored role
   // map, so that every sub-partition carries ONE main sweep instead of both CTAs' mains sitting on the same two:
   //   8 warps:  rot 0: MF 0  MB 1  LF 2  LB 3  workers 4..7     rot 1: MF 2  MB 3  LF 0  LB 1  workers 4..7
   //   10 warps: rot 0: MF 0  MB 1  LF 8  LB 9  workers 2..7     rot 1: MF 2  MB 3  LF 8  LB 9  workers 0,1,4..7
   if (tid == 0) {
+    const unsigned smid = (unsigned)first_draw[1];
 #ifdef SSD_EMU
-    sc->rot = (int)(blockIdx.x & 1u);
+    const unsigned slot = blockIdx.x & 1u;
 #else
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    sc->rot = (int)(atomicAdd(P.sm_slot + smid, 1u) & 1u) & P.rotate;
+    const unsigned slot = atomicAdd(P.sm_slot + smid, 1u) & 1u;  // working CTAs only
+    if (slot == 0u) *reinterpret_cast<volatile unsigned*>(P.sm_slot + 256 + smid) = (unsigned)CLS + 1u;
 #endif
+    sc->rot = (int)slot & P.rotate;
+    sc->second = (int)slot;
+    // checkpoint region: as many exist as CTAs of these kernels can be resident (two per SM) or, if that is fewer,
+    // as there are utterances.  Few utterances: first come, first served.  Otherwise the SM's two regions are taken
+    // and returned (a CTA of another width may follow on this SM while others still run elsewhere).
+    int region;
+    if (!P.region_by_sm) {
+      region = (int)atomicAdd(P.counter + 2, 1u);
+    } else {
+      unsigned* busy = P.sm_slot + 512 + 2 * smid;
+      for (region = -1; region < 0;) {
+        if (atomicCAS(busy, 0u, 1u) == 0u) region = (int)(2 * smid);
+        else if (atomicCAS(busy + 1, 0u, 1u) == 0u) region = (int)(2 * smid + 1);
+#ifndef SSD_EMU
+        else __nanosleep(200);
+#endif
+      }
+    }
+    sc->region = region;
   }
   __syncthreads();
+  unsigned char* ckpt_cta = P.ckpt + (size_t)sc->region * P.ckpt_cta_bytes;
   int role;  // 0 MF, 1 MB, 2 LF, 3 LB, 4 + w: worker w
   {
     const int m0 = sc->rot ? 2 : 0;  // first main warp
@@ -1172,10 +1326,15 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
 
   for (;;) {
     if (tid == 0) {
-      const int u = (int)atomicAdd(P.counter, 1u);
-      sc->utt = u;
-      if (u < P.B) {
-        const int b = P.order ? P.order[u] : u;
+      int u = first_draw[0];  // the draw that admitted this CTA
+      first_draw[0] = -1;
+      if (u < 0) {
+        u = (int)atomicAdd(my_ctr, 1u);
+        if (u < n_cls) u = (int)atomicAdd(my_ctr + 1, 1u);
+      }
+      sc->utt = u < n_cls ? 0 : P.B;
+      if (u < n_cls) {
+        const int b = my_list[u];
         const int64_t tl = P.in_len[b], sl = P.tg_len[b];
         const bool bad = tl < 0 || tl > P.T || sl < 0 || sl > P.S_max;
         sc->b = b;
@@ -1193,6 +1352,15 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     __syncthreads();
     if (sc->utt >= P.B) break;
     const int b = sc->b, S = sc->S;
+#if defined(SSD_LOSS_UTTRACE) && !defined(SSD_EMU)
+    if (P.tlog && tid == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.tlog[4 * b + 0] = t;
+      P.tlog[4 * b + 2] = first_draw[1];
+      P.tlog[4 * b + 3] = NC;
+    }
+#endif
     if (P.late_worker && uiter > 0u) {  // the previous utterance's late worker had its rows over the sweeps' rings
       for (int i = tid; i < 2 * F_NP * F_K; i += F_THREADS) {
         const int blk = i / F_K, r = i - blk * F_K;
@@ -1287,15 +1455,27 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
       const int f = sc->uflag;
       P.flags[b] = f;
       if (f) atomicAdd(P.counter + 1, 1u);
+#if defined(SSD_LOSS_UTTRACE) && !defined(SSD_EMU)
+      if (P.tlog) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.tlog[4 * b + 1] = t;
+      }
+#endif
     }
     __syncthreads();  // label tables and scalars are rebuilt for the next utterance
+  }
+  if (P.region_by_sm && tid == 0) {
+    __threadfence();
+    atomicExch(P.sm_slot + 512 + sc->region, 0u);
   }
 }
 
 // ------------------------------------------------------------------ host side
 struct FastPlan {
-  int NC, RS, grid, nb_max;
+  int NC, RS, grid, nb_max, regions;
   size_t smem, ckpt_cta_bytes, ckpt_rec_bytes, ws_bytes;
+  size_t off_flags, off_sm, off_cls, off_list, off_ckpt, off_tlog;
 };
 
 static int fast_env_int(const char* name, int dflt) {
@@ -1318,30 +1498,31 @@ static bool fast_plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, FastPl
   if (fast_env_int("SSD_LOSS_EXACT", 0)) return false;  // force the fp64 path (tests, comparisons)
   if (S_max > 255 || V > 128 || T < 1 || B < 1) return false;
   const int need = (int)((2 * S_max + 1 + 31) / 32);
-  const int buckets[4] = {4, 8, 12, 16};
-  pl.NC = 0;
-  for (int i = 0; i < 4 && !pl.NC; ++i)
-    if (need <= buckets[i]) pl.NC = buckets[i];
-  if (need <= 14 && need > 12) pl.NC = 14;
-  {  // tuning knob: force a wider strip than the lattice needs
-    const int nc = fast_env_int("SSD_LOSS_NC", 0);
-    if (nc >= pl.NC && (nc == 4 || nc == 8 || nc == 12 || nc == 14 || nc == 16)) pl.NC = nc;
-  }
-  if (!pl.NC) return false;
+  if (need > 16) return false;
+  pl.NC = fast_width_of(fast_class_of(need));  // the widest strip of the launch: shared memory is laid out for it
   const int cells = 32 * pl.NC, stage = F_SPAD + 32 + 4;
   pl.RS = ((cells > stage ? cells : stage) + 3) & ~3;
   pl.nb_max = (int)((T + F_K - 1) / F_K);
   pl.smem = fast_smem_layout((int)V, pl.RS, (int)S_max + 4, pl.nb_max).total;
   if (pl.smem > 113 * 1024) return false;
   const int64_t slots = (int64_t)fast_device_sms() * 2;
-  pl.grid = (int)(B < slots ? B : slots);
+  pl.grid = (int)(B < slots ? B : slots);  // per strip-width kernel; CTAs beyond a width's utterance count leave at once
+  pl.regions = pl.grid;
   {  // test knob: fewer CTAs than utterances, so that a CTA walks through several of them
     const int cap = fast_env_int("SSD_LOSS_GRID", 0);
     if (cap > 0 && cap < pl.grid) pl.grid = cap;
   }
   pl.ckpt_rec_bytes = (size_t)pl.NC * 32 * 4 + 128;
   pl.ckpt_cta_bytes = (size_t)2 * pl.nb_max * pl.ckpt_rec_bytes;
-  pl.ws_bytes = 256 + 4096 + (((size_t)B * 4 + 255) & ~(size_t)255) + (size_t)pl.grid * pl.ckpt_cta_bytes + (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t o = 256;
+  pl.off_flags = o; o += al((size_t)B * 4);
+  pl.off_sm = o; o += 4096;
+  pl.off_cls = o; o += 256;
+  pl.off_list = o; o += al((size_t)B * 4);
+  pl.off_ckpt = o; o += (size_t)pl.regions * pl.ckpt_cta_bytes;
+  pl.off_tlog = o; o += (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8;
+  pl.ws_bytes = o;
   return true;
 }
 
@@ -1351,18 +1532,27 @@ size_t loss_fast_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max)
 }
 
 template <int NC>
-static int loss_fast_launch_t(FastParams& P, const FastPlan& pl, cudaStream_t stream) {
+static int loss_fast_launch_t(const FastParams& P, const FastPlan& pl, cudaStream_t stream) {
   auto kfn = loss_fast_kernel<NC>;
 #ifndef SSD_EMU
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss(fast): cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
-  e = cudaMemsetAsync(P.counter, 0, 256, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(P.sm_slot, 0, 4096, stream);
-  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss(fast): cudaMemsetAsync: %s", cudaGetErrorString(e));
+  // programmatic stream serialisation: this kernel may start as soon as its predecessor in the stream lets it
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl.grid);
+  cfg.blockDim = dim3(F_THREADS);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kfn, P);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss_fast_kernel<%d>: %s", NC, cudaGetErrorString(e));
 #else
-  P.counter[0] = P.counter[1] = 0u;
-#endif
   SSD_LAUNCH(kfn, (unsigned)pl.grid, F_THREADS, pl.smem, stream, P);
+#endif
   return check_launch("loss_fast_kernel");
 }
 
@@ -1375,17 +1565,22 @@ int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int6
   FastPlan pl;
   if (!fast_plan_for(B, T, V, S_max, pl)) return SSD_ERR_UNSUPPORTED;
   if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
+  (void)order;  // the prepass groups and orders the utterances on the device (by strip width, then by frames)
   FastParams P;
   P.lp = lp; P.lse = lse; P.lse_stride = lse_stride; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
-  P.in_len = in_len; P.tg_len = tg_len; P.order = order;
+  P.in_len = in_len; P.tg_len = tg_len; P.order = nullptr;
   P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;
   P.nll = nll; P.grad = grad;
   unsigned char* w = reinterpret_cast<unsigned char*>(ws);
   P.counter = reinterpret_cast<unsigned*>(w);
-  P.flags = reinterpret_cast<int*>(w + 256);
-  P.sm_slot = reinterpret_cast<unsigned*>(w + 256 + (((size_t)B * 4 + 255) & ~(size_t)255));
-  P.ckpt = w + 256 + (((size_t)B * 4 + 255) & ~(size_t)255) + 4096;
+  P.flags = reinterpret_cast<int*>(w + pl.off_flags);
+  P.sm_slot = reinterpret_cast<unsigned*>(w + pl.off_sm);
+  int* cls = reinterpret_cast<int*>(w + pl.off_cls);
+  P.cls_start = cls;
+  P.cls_count = cls + 8;
+  P.cls_list = reinterpret_cast<int*>(w + pl.off_list);
+  P.ckpt = w + pl.off_ckpt;
   P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nb_max = pl.nb_max;
   P.RS = pl.RS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
@@ -1397,16 +1592,56 @@ int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int6
     P.late_worker = fast_env_int("SSD_LOSS_NOLATE", 0) ? 0 : (int)(2 * m.main_bytes / m.worker_bytes);
     if (P.late_worker > 2) P.late_worker = 2;
   }
-  P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.ws_bytes - (size_t)(F_THREADS / 32) * F_TLOG_N * F_TLOG_S * 8) : nullptr;
+  P.tlog = (fast_env_int("SSD_LOSS_DBG", 0) & 8) ? reinterpret_cast<long long*>(w + pl.off_tlog) : nullptr;
+  P.region_by_sm = B > pl.regions ? 1 : 0;
   *flags = P.flags;
   *nflag = P.counter + 1;
-  switch (pl.NC) {
-    case 4: return loss_fast_launch_t<4>(P, pl, stream);
-    case 8: return loss_fast_launch_t<8>(P, pl, stream);
-    case 12: return loss_fast_launch_t<12>(P, pl, stream);
-    case 14: return loss_fast_launch_t<14>(P, pl, stream);
-    default: return loss_fast_launch_t<16>(P, pl, stream);
+
+  PrepassParams Q;
+  Q.in_len = in_len; Q.tg_len = tg_len; Q.B = (int)B; Q.T = T; Q.S_max = (int)S_max; Q.nc_max = pl.NC;
+  // Per-utterance strip widths pay when the SMs are busy for several rounds (measured on B200, T=1000, S~U[50,200]:
+  // B=1024 -11 %, B=4096 -24 %).  With at most two utterances per SM the launch lasts as long as its slowest pair, whose
+  // time hardly depends on the width (sweeps are ~25 % of the instructions), and CTAs of DIFFERENT kernels sharing an
+  // SM run slower than two of the same one (instruction cache): B=256 took 432 us against 342 us.  So small batches
+  // run every utterance at the launch-wide width, in one kernel.
+  Q.nc_min = B > 4 * (int64_t)fast_device_sms() ? 4 : pl.NC;
+  {  // tuning / test knobs: force one or the other scheme, or a minimum strip width
+    const int multi = fast_env_int("SSD_LOSS_MULTI", -1);
+    if (multi == 1) Q.nc_min = 4;
+    if (multi == 0 || fast_env_int("SSD_LOSS_ONEWIDTH", 0)) Q.nc_min = pl.NC;
+    const int nc = fast_env_int("SSD_LOSS_NC", 0);
+    if (nc >= 4 && nc <= pl.NC) Q.nc_min = fast_width_of(fast_class_of(nc));
   }
+  Q.rank = B <= F_RANK_MAX ? 1 : 0;
+  Q.list = const_cast<int*>(P.cls_list); Q.start = cls; Q.count = cls + 8;
+  P.ranked = (Q.rank && !fast_env_int("SSD_LOSS_NODEAL", 0)) ? 1 : 0;
+#ifndef SSD_EMU
+  cudaError_t e = cudaMemsetAsync(P.counter, 0, 256, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(P.sm_slot, 0, 4096, stream);
+  if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss(fast): cudaMemsetAsync: %s", cudaGetErrorString(e));
+#else
+  for (int i = 0; i < 64; ++i) P.counter[i] = 0u;
+  for (int i = 0; i < 1024; ++i) P.sm_slot[i] = 0u;
+#endif
+  SSD_LAUNCH(loss_fast_prepass_kernel, 1u, 1024, 0, stream, Q);
+  int rc = check_launch("loss_fast_prepass_kernel");
+  if (rc) return rc;
+  // widest first: its utterances are the longest-running ones
+  const int c_hi = fast_class_of(pl.NC), c_lo = fast_class_of(Q.nc_min);
+  for (int c = c_hi; c >= c_lo; --c) {
+    P.pdl_wait = c == c_hi ? 1 : 0;
+    switch (c) {
+      case 0: rc = loss_fast_launch_t<4>(P, pl, stream); break;
+      case 1: rc = loss_fast_launch_t<6>(P, pl, stream); break;
+      case 2: rc = loss_fast_launch_t<8>(P, pl, stream); break;
+      case 3: rc = loss_fast_launch_t<10>(P, pl, stream); break;
+      case 4: rc = loss_fast_launch_t<12>(P, pl, stream); break;
+      case 5: rc = loss_fast_launch_t<14>(P, pl, stream); break;
+      default: rc = loss_fast_launch_t<16>(P, pl, stream); break;
+    }
+    if (rc) return rc;
+  }
+  return SSD_OK;
 }
 
 }  // namespace ssd

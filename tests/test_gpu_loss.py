@@ -348,3 +348,33 @@ def test_two_streams_do_not_share_scratch():
     for o1, o2 in outs:
         assert torch.equal(o1[0], ra[0]) and torch.equal(o1[1], ra[1])
         assert torch.equal(o2[0], rb[0]) and torch.equal(o2[1], rb[1])
+
+
+@pytest.mark.timeout(240)
+def test_per_utterance_strip_widths(monkeypatch):
+    """One kernel per strip width (prepass + programmatic dependent launches; the default above 4 utterances per SM,
+    forced here for a small batch too): every class of target length in one batch, ragged inputs, rows the fast path
+    refuses.  Against the exact fp64 kernel, and the two schemes against each other."""
+    B, T, S = 900, 200, 250
+    g = torch.Generator().manual_seed(11)
+    tl = torch.randint(1, S + 1, (B,), generator=g)
+    il = synth.ragged_lengths(B, T, 12)
+    tg = torch.randint(2, 48, (B, S), generator=g) * (torch.arange(S)[None, :] < tl[:, None])
+    il[3], tl[4] = 0, 0
+    lp = synth.flat(B, T, 13).cuda()
+    monkeypatch.setenv("SSD_LOSS_EXACT", "1")
+    nll_x, g_x = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
+    monkeypatch.delenv("SSD_LOSS_EXACT")
+    fin = torch.isfinite(nll_x) & (nll_x != 0)
+    outs = {}
+    for multi, n in (("1", B), ("0", B), ("1", 40), ("0", 40)):
+        monkeypatch.setenv("SSD_LOSS_MULTI", multi)
+        nll, gr = ops.ctc_loss_fwd_bwd(lp[:n], il[:n], tg[:n], tl[:n], blank=1, mean_denominator=B)
+        f = fin[:n]
+        assert ((nll[f] - nll_x[:n][f]).abs() / nll_x[:n][f].abs()).max().item() < 5e-6, (multi, n)
+        assert (gr - g_x[:n]).abs().max().item() <= RTOL * g_x[:n].abs().max().item(), (multi, n)
+        outs[(multi, n)] = (nll, gr)
+    monkeypatch.delenv("SSD_LOSS_MULTI")
+    # the default for this batch (900 > 4 x 148) is the per-width scheme: same bits as forcing it
+    nll, gr = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
+    assert torch.equal(nll, outs[("1", B)][0]) and torch.equal(gr, outs[("1", B)][1])
