@@ -165,6 +165,11 @@ int ssd_ctc_loss_from_logits(const float* logits, int64_t B, int64_t T, int64_t 
 int ssd_row_logsumexp(const float* x, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t, float* lse,
                       int64_t lse_stride, void* stream);
 
+/* The two scalars of the batch-mean loss: out[0] = sum_b nll[b] / max(target_lengths[b], 1) (fp64, fixed summation
+ * order), out[1] = B.  mean = out[0] / out[1] is nn.CTCLoss's reduction='mean' (src/models/losses.py:28,56); data-parallel
+ * ranks all-reduce the pair.  out: device pointer to two doubles. */
+int ssd_ctc_loss_parts(const float* nll, const int64_t* target_lengths, int64_t B, double* out, void* stream);
+
 /* x[i] *= *g / expected for i < n -- unless *g == expected, in which case nothing but *g is read.
  * autograd's backward of the fused loss: the gradient was written with the scalar the caller expects
  * upstream (lambda_ctc of src/models/losses.py:104); the device-side test replaces a host

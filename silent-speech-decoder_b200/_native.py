@@ -28,6 +28,7 @@ SIGNATURES = {
     "ssd_ctc_loss_from_logits": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "ssd_row_logsumexp": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
     "ssd_scale_if": (C.c_int, [_P, _I64, _P, _F32, _P]),
+    "ssd_ctc_loss_parts": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ssd_ctc_loss_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_ctc_loss_fallback_counter_offset": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_edit_counts": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),

@@ -110,6 +110,35 @@ __global__ void __launch_bounds__(256) scale_if_kernel(float* __restrict__ x, in
   }
 }
 
+// out[0] = sum_b nll[b] / max(target_lengths[b], 1) in fp64, out[1] = B: the two scalars of the batch-mean loss
+// (torch's reduction='mean' of nn.CTCLoss, reference losses.py:28,56) and of its data-parallel all-reduce.  One CTA,
+// fixed summation order: the same bits on every run.
+__global__ void __launch_bounds__(256) loss_parts_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tg_len, int64_t B,
+                                                         double* __restrict__ out) {
+  __shared__ double part[256];
+  const int tid = (int)threadIdx.x;
+  double acc = 0.0;
+  for (int64_t b = tid; b < B; b += 256) {
+    const int64_t s = tg_len[b];
+    acc += (double)nll[b] / (double)(s > 1 ? s : 1);
+  }
+  part[tid] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) part[tid] += part[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[0] = part[0];
+    out[1] = (double)B;
+  }
+}
+
+int loss_parts_launch(const float* nll, const int64_t* tg_len, int64_t B, double* out, cudaStream_t stream) {
+  SSD_LAUNCH(loss_parts_kernel, 1u, 256, 0, stream, nll, tg_len, B, out);
+  return check_launch("loss_parts_kernel");
+}
+
 int scale_if_launch(float* x, int64_t n, const float* g, float expected, cudaStream_t stream) {
   if (n == 0) return SSD_OK;
 #ifdef SSD_EMU

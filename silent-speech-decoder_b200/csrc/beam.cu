@@ -45,7 +45,7 @@ namespace ssd {
 #endif
 constexpr int BM_CONS = SSD_BEAM_CONS;    // consumer threads (a per-frame phase rarely has more than ~100 items)
 constexpr int BM_THREADS = BM_CONS + 32;  // + producer warp
-constexpr int BM_CHUNK = 16;             // frames per TMA chunk
+constexpr int BM_CHUNK = 8;              // frames per TMA chunk (two buffers; shared memory decides the CTAs per SM)
 constexpr int BAR_CONS = 1;              // named barrier: consumers only
 constexpr int BAR_FRAME = 2;             // named barrier: consumers + producer, once per frame
 constexpr int LBL_NONE = 255;
@@ -150,7 +150,14 @@ __device__ __forceinline__ unsigned char* carve(unsigned char*& p, size_t bytes)
   p += (bytes + 15) & ~(size_t)15;
   return r;
 }
-__device__ __forceinline__ void carve_prefix(unsigned char*& p, Prefix& a, int W) {
+__host__ __device__ inline size_t prefix_gen_bytes(int W) {
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  return 7 * al(8 * (size_t)W) + 3 * al(4 * (size_t)W);
+}
+// the table of generation g starts at base + g * prefix_gen_bytes(W): computed, not looked up in an array of
+// structs (which the compiler keeps in local memory once it is indexed by a run-time g)
+__device__ __forceinline__ Prefix prefix_at(unsigned char* p, int W) {
+  Prefix a;
   a.H = (uint64_t*)carve(p, 8 * W);
   a.Hpar = (uint64_t*)carve(p, 8 * W);
   a.Hstrip = (uint64_t*)carve(p, 8 * W);
@@ -161,21 +168,29 @@ __device__ __forceinline__ void carve_prefix(unsigned char*& p, Prefix& a, int W
   a.node = (uint32_t*)carve(p, 4 * W);
   a.last = (int*)carve(p, 4 * W);
   a.len = (int*)carve(p, 4 * W);
+  return a;
+}
+
+// slots of the per-frame history-key table (pow2, >= 2 * W when the scratch it overlays allows)
+__host__ __device__ inline int beam_hk_slots(int W, int NCAND) {
+  int n = 4;
+  while (n < 2 * W && 12 * (2 * n) <= 8 * NCAND) n <<= 1;
+  return n;
 }
 
 __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND) {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t s = 0;
-  s += 2 * (7 * al(8 * (size_t)W) + 3 * al(4 * (size_t)W));  // prefix tables
-  s += 4 * al(8 * (size_t)W);                               // tot, newb, newnb, ext_in
-  s += 6 * al(4 * (size_t)W);                               // par, rnk, rank2p, rowoff, keepflags, slot
+  s += 2 * prefix_gen_bytes(W);                              // prefix tables, two generations
+  s += 3 * al(8 * (size_t)W);                               // tot, newb, newnb
+  s += 5 * al(4 * (size_t)W);                               // par, rank2p, rowoff, keepflags, slot
   s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
   s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // candidate score, desc
-  s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // alive score, alive idx
-  s += 2 * al(4 * (size_t)NCAND) + al(4 * 256);             // bucket of each alive entry, boundary list, histogram
+  s += al(4 * (size_t)NCAND);                               // alive idx
+  s += 2 * al(4 * (size_t)NCAND) + al(4 * 256);             // bucket of each alive entry, boundary list (also: history-key table), histogram
   s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // the W survivors of the bucket cut
   s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
-  s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // sel_hk, sel_lc
+  s += al(8 * (size_t)(W + 1));                             // sel_hk
   s += 2 * (al(4 * (size_t)VL) + al(VL));                   // frame records: rl[VL], cs[VL] (x2)
   s += al(4 * (size_t)VL);                                  // lab2voc
   s += 2 * al((size_t)BM_CHUNK * V * 4);                    // raw log-prob chunks
@@ -316,21 +331,19 @@ __device__ __forceinline__ int table_find(const unsigned long long* keys, const 
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel(const BeamParams P) {
+__global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
   const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
 
-  Prefix gen[2];
   const int WC = P.W;  // capacity: every table below is sized for the widest setting of the launch
-  carve_prefix(sp, gen[0], WC);
-  carve_prefix(sp, gen[1], WC);
+  unsigned char* const gen_base = sp;
+  const size_t gen_stride = prefix_gen_bytes(WC);
+  sp += 2 * gen_stride;
   double* tot = (double*)carve(sp, 8 * WC);
   double* newb = (double*)carve(sp, 8 * WC);
   double* newnb = (double*)carve(sp, 8 * WC);
-  double* ext_in = (double*)carve(sp, 8 * WC);
   int* par = (int*)carve(sp, 4 * WC);
-  int* rnk = (int*)carve(sp, 4 * WC);
   int* rank2p = (int*)carve(sp, 4 * WC);
   int* rowoff = (int*)carve(sp, 4 * WC);
   int* keepf = (int*)carve(sp, 4 * WC);
@@ -339,9 +352,8 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
   int* tvals = (int*)carve(sp, 4 * TS);
   double* cscore = (double*)carve(sp, 8 * NCAND);
   uint32_t* cdesc = (uint32_t*)carve(sp, 4 * NCAND);
-  double* ascore = (double*)carve(sp, 8 * NCAND);
   int* aidx = (int*)carve(sp, 4 * NCAND);
-  int* abkt = (int*)carve(sp, 4 * NCAND);
+  int* abkt = (int*)carve(sp, 4 * NCAND);   // abkt and blist are contiguous: after the cut they hold the history-key table
   int* blist = (int*)carve(sp, 4 * NCAND);
   int* hist = (int*)carve(sp, 4 * 256);
   double* bscore = (double*)carve(sp, 8 * (WC + 1));
@@ -350,17 +362,27 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
   int* sel_keep = (int*)carve(sp, 4 * (WC + 1));
   int* sel_slot = (int*)carve(sp, 4 * (WC + 1));
   uint64_t* sel_hk = (uint64_t*)carve(sp, 8 * (WC + 1));
-  int* sel_lc = (int*)carve(sp, 4 * (WC + 1));
-  FrameRec fr[2];
-  for (int i = 0; i < 2; ++i) {
-    fr[i].rl = (float*)carve(sp, 4 * VL);
-    fr[i].cs = (unsigned char*)carve(sp, VL);
-  }
+  float* const rl_base = (float*)carve(sp, 4 * VL);
+  unsigned char* const cs_base = (unsigned char*)carve(sp, VL);
+  float* const rl_1 = (float*)carve(sp, 4 * VL);
+  unsigned char* const cs_1 = (unsigned char*)carve(sp, VL);
+  const ptrdiff_t rl_stride = rl_1 - rl_base, cs_stride = cs_1 - cs_base;
+  auto frame_rec = [&](int i) {
+    FrameRec f;
+    f.rl = rl_base + (i & 1) * rl_stride;
+    f.cs = cs_base + (i & 1) * cs_stride;
+    return f;
+  };
   int* lab2voc = (int*)carve(sp, 4 * VL);
-  float* chunk[2];
-  chunk[0] = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
-  chunk[1] = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  float* const chunk0 = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  float* const chunk1 = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  const ptrdiff_t chunk_stride = chunk1 - chunk0;
+  auto chunk_buf = [&](int c) { return chunk0 + (c & 1) * chunk_stride; };
   Scal* sc = (Scal*)carve(sp, sizeof(Scal));
+  // history-key table over the (by then free) abkt/blist scratch: keys, then the best rank per key
+  const int HKS = beam_hk_slots(WC, NCAND);
+  unsigned long long* hk_keys = reinterpret_cast<unsigned long long*>(abkt);
+  int* hk_rank = reinterpret_cast<int*>(hk_keys + HKS);
 
   const int tid = (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
 
     // ---------------- initial beam: the empty prefix, blank-ended with score 0
     if (tid == 0) {
-      Prefix& a = gen[0];
+      const Prefix a = prefix_at(gen_base, WC);
       a.H[0] = hmix(0x243F6A8885A308D3ull, 0u);
       a.Hpar[0] = 0ull;  // never a key
       a.Hstrip[0] = a.H[0];
@@ -422,12 +444,12 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
     }
     for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
     __syncthreads();
-    if (tid == 0) table_insert(tkeys, tvals, tmask, gen[0].H[0], 0);
+    if (tid == 0) table_insert(tkeys, tvals, tmask, prefix_at(gen_base, WC).H[0], 0);
 
     // ---------------- producer prologue: chunk 0 (+1 in flight), frame 0 record
     auto load_chunk = [&](int c) {  // producer warp
       const int rows = min(BM_CHUNK, len - c * BM_CHUNK);
-      float* dst = chunk[c & 1];
+      float* dst = chunk_buf(c);
       const float* src = base + (int64_t)c * BM_CHUNK * P.st;
       if (P.use_tma) {
         if (lane == 0) {
@@ -453,7 +475,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
       load_chunk(0);
       if (nchunks > 1) load_chunk(1);
       wait_chunk(0);
-      condition_frame(chunk[0], P, s_bias, s_tmin, lab2voc, fr[0], &sc->nc1[0]);
+      condition_frame(chunk0, P, s_bias, s_tmin, lab2voc, frame_rec(0), &sc->nc1[0]);
     }
     __syncthreads();
 
@@ -469,19 +491,60 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
             if (c + 1 < nchunks) load_chunk(c + 1);
             wait_chunk(c);
           }
-          condition_frame(chunk[c & 1] + r * P.V, P, s_bias, s_tmin, lab2voc, fr[tn & 1], &sc->nc1[tn & 1]);
+          condition_frame(chunk_buf(c) + r * P.V, P, s_bias, s_tmin, lab2voc, frame_rec(tn), &sc->nc1[tn & 1]);
         }
         bar_sync(BAR_FRAME, BM_THREADS);
         continue;
       }
       // ============================ consumers ============================
-      const Prefix& A = gen[g];
-      const Prefix& N = gen[g ^ 1];
-      const FrameRec F = fr[t & 1];
+      const Prefix A = prefix_at(gen_base + g * gen_stride, WC);
+      const Prefix N = prefix_at(gen_base + (g ^ 1) * gen_stride, WC);
+      const FrameRec F = frame_rec(t);
       const int nc1 = sc->nc1[t & 1];
       const int np = sc->np;
       const unsigned node0 = sc->nodes_used;  // read here: thread 0 rewrites it in phase 6b
       SSD_ASSERT(np >= 1 && np <= W);
+
+      // ---- blank-only frame: the candidate set is {blank} (a confident blank: most frames of a trained CTC model).
+      // Every prefix then keeps exactly its blank-ended entry, scored tot + r_blank; nothing is proposed, the ranking
+      // does not change.  If none falls below the relative cut and no two share a history key, the general path
+      // would copy every prefix to the same slot of the next generation: update the scores in place instead and
+      // leave the hash table alone.  Otherwise (rare) the general path below does the frame.
+      if (nc1 == 0 && F.rl[0] != -INFINITY) {
+        const double rb = (double)F.rl[0];
+        double m = neg_inf();
+        for (int p = tid; p < np; p += BM_CONS) {
+          const double v = lse2(A.sb[p], A.snb[p]) + rb;
+          newb[p] = v;
+          m = v > m ? v : m;
+          sel_hk[p] = hmix(hmix(A.hl[p] ^ hmix(A.ho[p], 0x5bu), 0xa7u), 0x100u);  // phase 5's key with last char = blank
+        }
+        m = warp_max_d(m);
+        if (lane == 0) sc->wmax[warp] = m;
+        if (tid == 0) sc->n_b = 0;
+        cons_sync();
+        double mm = sc->wmax[0];
+        for (int w = 1; w < BM_CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
+        const double cut = mm + (double)s_prune;
+        bool general = false;
+        for (int p = tid; p < np; p += BM_CONS) {
+          const double v = newb[p];
+          if (!(v >= cut) || v == -INFINITY) general = true;
+          const uint64_t hk = sel_hk[p];
+          for (int q = 0; q < np; ++q)
+            if (q != p && sel_hk[q] == hk) general = true;
+        }
+        if (general) sc->n_b = 1;
+        cons_sync();
+        if (sc->n_b == 0) {
+          for (int p = tid; p < np; p += BM_CONS) {
+            A.sb[p] = newb[p];
+            A.snb[p] = neg_inf();
+          }
+          bar_sync(BAR_FRAME, BM_THREADS);  // same generation, same table; frame t+1's record is visible
+          continue;
+        }
+      }
 
       // ---- phase 1: tot, parent slot
       for (int p = tid; p < np; p += BM_CONS) {
@@ -499,7 +562,6 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
           const double o = tot[q];
           rk += (o > mine || (o == mine && q < p)) ? 1 : 0;
         }
-        rnk[p] = rk;
         rank2p[rk] = p;
         const int e = A.last[p];
         const float r_e = (e != LBL_NONE) ? F.rl[e] : -INFINITY;
@@ -607,8 +669,11 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
           }
           if (alive) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
-            ascore[pos] = cscore[k];
             aidx[pos] = k;
+            if (pos <= W) {  // at most W alive (the usual case): this already is the list that gets ranked
+              bscore[pos] = cscore[k];
+              bidx[pos] = k;
+            }
           }
           running += totc;
           cons_sync();
@@ -623,9 +688,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
       // over [cutoff, max] -- everything in buckets above the boundary bucket is in, the boundary
       // bucket is resolved by exact rank among its few members -- then rank only those W.
       // Same ordering rule as a full rank count (score desc, candidate index asc), so same result.
-      const double* rs = ascore;  // entries to rank: (rs[i], ri[i]), i < n_rank
-      const int* ri = aidx;
-      int n_rank = n_alive;
+      int n_rank = n_alive;  // entries to rank: (bscore[i], bidx[i]), i < n_rank
       if (n_alive > W) {
         for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
@@ -633,7 +696,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
         const double top = cutoff - (double)s_prune;
         const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
         for (int i = tid; i < n_alive; i += BM_CONS) {
-          int b = (int)((top - ascore[i]) * scale);
+          int b = (int)((top - cscore[aidx[i]]) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
           abkt[i] = b;
           atomicAdd(&hist[b], 1);
@@ -666,11 +729,11 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
         const int m = sc->n_b;
         for (int t = tid; t < m; t += BM_CONS) {
           const int i = blist[t];
-          const double mine = ascore[i];
+          const double mine = cscore[aidx[i]];
           int rk = 0;
           for (int u = 0; u < m; ++u) {
             const int j = blist[u];
-            const double o = ascore[j];
+            const double o = cscore[aidx[j]];
             rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
           }
           abkt[i] = rk < need ? -1 : 256;  // in / out
@@ -694,7 +757,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
             }
             if (in) {
               const int pos = off + __popc(mk & ((1u << lane) - 1u));
-              bscore[pos] = ascore[i];
+              bscore[pos] = cscore[aidx[i]];
               bidx[pos] = aidx[i];
             }
             running += totc;
@@ -702,18 +765,16 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
           }
           SSD_ASSERT(running == W);
         }
-        rs = bscore;
-        ri = bidx;
         n_rank = W;
       }
       for (int i = tid; i < n_rank; i += BM_CONS) {
-        const double mine = rs[i];
+        const double mine = bscore[i];
         int rk = 0;
         for (int j = 0; j < n_rank; ++j) {
-          const double o = rs[j];
+          const double o = bscore[j];
           rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
         }
-        if (rk < W) sel[rk] = ri[i];
+        if (rk < W) sel[rk] = bidx[i];
       }
       cons_sync();
 
@@ -734,12 +795,28 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
         sel_hk[r] = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);
       }
       for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
+      // best rank per history key through a small hash table (over scratch the cut above no longer needs): an entry
+      // survives iff it holds the best rank of its key.  Replaces a scan of every better-ranked entry (16 % of the
+      // kernel's instructions at config 3).
+      for (int i = tid; i < HKS; i += BM_CONS) {
+        hk_keys[i] = 0ull;
+        hk_rank[i] = 0x7fffffff;
+      }
       cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
-        const uint64_t hk = sel_hk[r];
-        int keep = 1;
-        for (int q = 0; q < r; ++q)
-          if (sel_hk[q] == hk) { keep = 0; break; }
+        const unsigned long long hk = (unsigned long long)sel_hk[r];  // never 0 (hmix)
+        int s_ = (int)(hk & (unsigned long long)(HKS - 1));
+        for (;;) {
+          const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, hk);
+          if (old == 0ull || old == hk) break;
+          s_ = (s_ + 1) & (HKS - 1);
+        }
+        atomicMin(&hk_rank[s_], r);
+        sel_slot[r] = s_;  // remembered for the read-back below (sel_slot is rewritten in phase 6a)
+      }
+      cons_sync();
+      for (int r = tid; r < n_sel; r += BM_CONS) {
+        int keep = hk_rank[sel_slot[r]] == r ? 1 : 0;
         const uint32_t d = cdesc[sel[r]];
         const int c = (int)(d & 0xFFu);
         if (keep && (c == 0 || c == 0xFE)) {
@@ -821,7 +898,7 @@ __global__ void __launch_bounds__(BM_THREADS, BM_CONS == 32 ? 8 : 6) beam_kernel
     // ---------------- finish: merge variants, pick the best text, emit labels
     __syncthreads();
     if (!producer) {
-      const Prefix& A = gen[g];
+      const Prefix A = prefix_at(gen_base + g * gen_stride, WC);
       const int np = sc->np;
       for (int p = tid; p < np; p += BM_CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
       cons_sync();

@@ -149,6 +149,12 @@ int ssd_ctc_loss_from_logits(const float* logits, int64_t B, int64_t T, int64_t 
                      zero_infinity, mean_denominator, grad_mul, nll, grad, workspace, off, (cudaStream_t)stream);
 }
 
+int ssd_ctc_loss_parts(const float* nll, const int64_t* target_lengths, int64_t B, double* out, void* stream) {
+  if (B < 0) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_parts: B < 0");
+  if (!out || (B > 0 && (!nll || !target_lengths))) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_loss_parts: NULL pointer");
+  return loss_parts_launch(nll, target_lengths, B, out, (cudaStream_t)stream);
+}
+
 int ssd_scale_if(float* x, int64_t n, const float* g, float expected, void* stream) {
   if (n < 0) return fail(SSD_ERR_BAD_ARG, "ssd_scale_if: n < 0");
   if (n > 0 && (!x || !g)) return fail(SSD_ERR_BAD_ARG, "ssd_scale_if: NULL pointer");

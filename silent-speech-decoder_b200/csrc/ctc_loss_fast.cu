@@ -182,6 +182,7 @@ struct FastParams {
   int ranked;            // cls_list is cost-ordered within a class: the second CTA of an SM draws from the cheap end
   int region_by_sm;      // 1: more utterances than checkpoint regions, a CTA takes one of its SM's two regions and returns it
   int pdl_wait;          // first class kernel after the prepass: wait for it (programmatic dependent launch)
+  int direct;            // 1: no prepass -- one kernel takes all B utterances in the caller's order (B <= checkpoint regions)
   int* flags;          // [B] non-zero = recompute on the exact path (1 not covered, 2 D1, 4 D2, 8 D3, 16 D4)
   unsigned char* ckpt; // per CTA: [2 dirs][nb_max] records
   size_t ckpt_cta_bytes, ckpt_rec_bytes;
@@ -1192,8 +1193,8 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
   if (P.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
-  const int n_cls = P.cls_count[CLS];
-  const int* my_list = P.cls_list + P.cls_start[CLS];
+  const int n_cls = P.direct ? P.B : P.cls_count[CLS];
+  const int* my_list = P.direct ? P.order : P.cls_list + P.cls_start[CLS];
   unsigned* my_ctr = P.counter + 16 + 4 * CLS;
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // Who works is decided by the FIRST DRAW, not by the block index: every width's kernel has as many CTAs as there are
@@ -1211,7 +1212,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     const unsigned here = *reinterpret_cast<volatile unsigned*>(P.sm_slot + smid);
-    if (here > 0u) {
+    if (here > 0u && !P.direct) {
       // a working CTA of the SAME width here: sharing its code in the instruction cache is worth more than an idle SM
       // is to a narrower width; of another width: everybody else first
       const unsigned other = *reinterpret_cast<volatile unsigned*>(P.sm_slot + 256 + smid);
@@ -1334,7 +1335,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
       }
       sc->utt = u < n_cls ? 0 : P.B;
       if (u < n_cls) {
-        const int b = my_list[u];
+        const int b = my_list ? my_list[u] : u;
         const int64_t tl = P.in_len[b], sl = P.tg_len[b];
         const bool bad = tl < 0 || tl > P.T || sl < 0 || sl > P.S_max;
         sc->b = b;
@@ -1565,11 +1566,12 @@ int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int6
   FastPlan pl;
   if (!fast_plan_for(B, T, V, S_max, pl)) return SSD_ERR_UNSUPPORTED;
   if (!ws || ws_bytes < pl.ws_bytes) return fail(SSD_ERR_WORKSPACE, "ssd_ctc_loss: workspace %zu bytes, need %zu", ws_bytes, pl.ws_bytes);
-  (void)order;  // the prepass groups and orders the utterances on the device (by strip width, then by frames)
+  // `order` is honoured by the direct scheme only; otherwise the prepass groups and orders the utterances on the device
+  // (by strip width, then by frames)
   FastParams P;
   P.lp = lp; P.lse = lse; P.lse_stride = lse_stride; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.targets = targets; P.tgt_stride = tgt_stride; P.S_max = (int)S_max;
-  P.in_len = in_len; P.tg_len = tg_len; P.order = nullptr;
+  P.in_len = in_len; P.tg_len = tg_len; P.order = order;
   P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;
   P.nll = nll; P.grad = grad;
   unsigned char* w = reinterpret_cast<unsigned char*>(ws);
@@ -1623,13 +1625,20 @@ int loss_fast_launch(const float* lp, const float* lse, int64_t lse_stride, int6
   for (int i = 0; i < 64; ++i) P.counter[i] = 0u;
   for (int i = 0; i < 1024; ++i) P.sm_slot[i] = 0u;
 #endif
-  SSD_LAUNCH(loss_fast_prepass_kernel, 1u, 1024, 0, stream, Q);
-  int rc = check_launch("loss_fast_prepass_kernel");
-  if (rc) return rc;
   // widest first: its utterances are the longest-running ones
   const int c_hi = fast_class_of(pl.NC), c_lo = fast_class_of(Q.nc_min);
+  // one width and a checkpoint region for every utterance: each CTA takes one utterance, nothing to group or rank
+  P.direct = (c_lo == c_hi && B <= pl.regions && pl.grid == pl.regions && !fast_env_int("SSD_LOSS_PREPASS", 0)) ? 1 : 0;
+  int rc = SSD_OK;
+  if (!P.direct) {
+    SSD_LAUNCH(loss_fast_prepass_kernel, 1u, 1024, 0, stream, Q);
+    rc = check_launch("loss_fast_prepass_kernel");
+    if (rc) return rc;
+  } else {
+    P.ranked = 0;
+  }
   for (int c = c_hi; c >= c_lo; --c) {
-    P.pdl_wait = c == c_hi ? 1 : 0;
+    P.pdl_wait = (c == c_hi && !P.direct) ? 1 : 0;
     switch (c) {
       case 0: rc = loss_fast_launch_t<4>(P, pl, stream); break;
       case 1: rc = loss_fast_launch_t<6>(P, pl, stream); break;

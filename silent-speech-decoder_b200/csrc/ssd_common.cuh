@@ -47,6 +47,7 @@ int loss_launch(const float* lp, const float* lse, int64_t lse_stride, int64_t B
 int row_lse_launch(const float* x, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, float* lse, int64_t lse_stride,
                    cudaStream_t stream);
 int scale_if_launch(float* x, int64_t n, const float* g, float expected, cudaStream_t stream);
+int loss_parts_launch(const float* nll, const int64_t* tg_len, int64_t B, double* out, cudaStream_t stream);
 
 int edit_launch(const int32_t* ref_tok, const int64_t* ref_off, const int32_t* hyp_tok, const int64_t* hyp_off, int64_t N,
                 int64_t max_ref_len, int64_t max_hyp_len, int32_t* counts, cudaStream_t stream);

@@ -105,24 +105,32 @@ def _rows_to_strings(tok: torch.Tensor, cnt: torch.Tensor, text: Sequence[str], 
 # kernel run while chunk k's ids come back and its strings are assembled on the host (the reference hands its
 # decoders CPU tensors, evaluate.py:299; at config 3 that is a 960 MB copy and ~20 ms of string work per call).
 PIPELINE_MIN_BYTES = 96 << 20
-PIPELINE_CHUNK = 1776  # utterances: twelve per SM, about two waves of resident beam CTAs
+PIPELINE_CHUNK = 0  # utterances per chunk; 0 = eight per SM (one wave of resident beam CTAs at width 50: measured best on B200)
+
+
+_PIPE_STREAMS: dict = {}
 
 
 def _pipelined(log_probs: torch.Tensor, lengths: torch.Tensor, launch, to_strings) -> List[str]:
     """``launch(x_dev, len_dev) -> tensors``; ``to_strings(*tensors) -> List[str]`` (does the D2H copies)."""
     B = log_probs.size(0)
-    big = (not log_probs.is_cuda) and log_probs.dim() == 3 and log_probs.numel() * 4 >= PIPELINE_MIN_BYTES and B >= 2 * PIPELINE_CHUNK
+    chunk = PIPELINE_CHUNK
+    if chunk <= 0 and not log_probs.is_cuda and torch.cuda.is_available():
+        chunk = 8 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    big = (not log_probs.is_cuda) and log_probs.dim() == 3 and log_probs.numel() * 4 >= PIPELINE_MIN_BYTES and chunk > 0 and B >= 2 * chunk
     if not big:
         return to_strings(*launch(log_probs, lengths))
     dev = ops._device(log_probs)
     ln = torch.as_tensor(lengths)
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = _PIPE_STREAMS.get(dev.index)
+    if streams is None:  # two streams per device, kept: the scratch buffers in ops are cached per stream
+        streams = _PIPE_STREAMS[dev.index] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     for s in streams:
         s.wait_stream(torch.cuda.current_stream(dev))
     out: List[str] = []
     pending = None
-    for k, lo in enumerate(range(0, B, PIPELINE_CHUNK)):
-        hi = min(B, lo + PIPELINE_CHUNK)
+    for k, lo in enumerate(range(0, B, chunk)):
+        hi = min(B, lo + chunk)
         s = streams[k & 1]
         with torch.cuda.stream(s):
             x = log_probs[lo:hi].to(dev, non_blocking=True)

@@ -116,7 +116,11 @@ def sharded_decode(decode_ids: Callable[[torch.Tensor, torch.Tensor], List[List[
 
 def _loss_parts(nll: torch.Tensor, target_lengths: torch.Tensor) -> torch.Tensor:
     # everything stays on the stream: no host-side scalar is copied in (that would synchronise the step)
-    s = (nll / target_lengths.to(nll.device).clamp_min(1)).sum(dtype=torch.float64)
+    if nll.is_cuda and nll.dim() == 1:
+        from . import ops
+
+        return ops.loss_parts(nll, target_lengths)  # one launch for both scalars
+    s = (nll / target_lengths.to(nll.device).clamp_min(1)).sum(dtype=torch.float64)  # host tensors (gloo tests)
     return torch.stack([s, torch.full_like(s, float(nll.numel()))])
 
 

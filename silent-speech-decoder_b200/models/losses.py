@@ -78,7 +78,8 @@ class _CTCFused(torch.autograd.Function):
         elif reduction == "sum":
             out = nll.sum()
         else:
-            out = (nll / target_lengths.to(device=nll.device).clamp_min(1).to(nll.dtype)).mean()
+            parts = ops.loss_parts(nll, target_lengths)  # [sum_b nll_b / max(S_b,1), B] in one launch
+            out = parts[0] / parts[1]
         out = out.to(x_tbv.dtype)
         return out if out.device == x_tbv.device else out.to(x_tbv.device)
 

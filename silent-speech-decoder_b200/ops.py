@@ -206,6 +206,22 @@ def scale_if(x: torch.Tensor, g: torch.Tensor, expected: float) -> None:
         LAUNCHES["aux"] += 1
 
 
+def loss_parts(nll: torch.Tensor, target_lengths: torch.Tensor) -> torch.Tensor:
+    """(2,) fp64 on the device: [sum_b nll_b / max(S_b, 1), B] -- one launch (``ssd_ctc_loss_parts``) instead of the
+    five elementwise/reduction kernels torch needs for the same two numbers."""
+    lib = _native.load()
+    dev = nll.device
+    with torch.cuda.device(dev):
+        x = nll.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        tl = _prep_lengths(target_lengths, x.numel(), dev)
+        out = torch.empty((2,), dtype=torch.float64, device=dev)
+        lib.check(lib.ssd_ctc_loss_parts(x.data_ptr(), tl.data_ptr(), x.numel(), out.data_ptr(), _stream_ptr(dev)))
+        LAUNCHES["aux"] += 1
+    return out
+
+
 _SCALARS: Dict[Tuple[int, float], torch.Tensor] = {}
 
 
