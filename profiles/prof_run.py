@@ -25,7 +25,7 @@ else:
     v = Vocab.default()
     kind = "flat" if what.endswith("flat") else "peaked"
     n = 2000
-    lp, ln = bench.cfg3_inputs(n, kind)
+    lp, ln = bench.decode_inputs(n, 500, kind, 1003)
     x, ln = lp.to(dev), ln.to(dev)
     _, space = ctc._beam_label_strings(v)
     for _ in range(reps):

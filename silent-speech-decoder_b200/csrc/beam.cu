@@ -109,6 +109,11 @@ __device__ __forceinline__ uint64_t hmix(uint64_t h, uint32_t c) {
   return x ? x : 1ull;
 }
 __device__ __forceinline__ double neg_inf() { return -INFINITY; }
+// doubles -> unsigned integers in the same order (-inf lowest; no NaN reaches this)
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const long long b = __double_as_longlong(v);
+  return b >= 0 ? (unsigned long long)b ^ 0x8000000000000000ull : ~(unsigned long long)b;
+}
 // fp64 logaddexp in upstream's form: hi + log(1 + exp(lo - hi))
 __device__ __forceinline__ double lse2(double a, double b) {
   const double hi = a >= b ? a : b, lo = a >= b ? b : a;
@@ -154,8 +159,29 @@ __host__ __device__ inline size_t prefix_gen_bytes(int W) {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   return 7 * al(8 * (size_t)W) + 3 * al(4 * (size_t)W);
 }
-// the table of generation g starts at base + g * prefix_gen_bytes(W): computed, not looked up in an array of
-// structs (which the compiler keeps in local memory once it is indexed by a run-time g)
+// The table of generation g starts at base + g * prefix_gen_bytes(W).  An array of two structs indexed by a run-time
+// g lives in local memory (20 LDL per thread and frame); pointers rebuilt every frame cost 7 % of the kernel's
+// instructions.  So: generation 0's pointers are set up once, and a view adds g's element offset in the subscript.
+template <class T>
+struct GenArr {
+  T* base;
+  int off;
+  __device__ __forceinline__ T& operator[](int i) const { return base[off + i]; }
+};
+struct PrefixView {
+  GenArr<uint64_t> H, Hpar, Hstrip, hl, ho;
+  GenArr<double> sb, snb;
+  GenArr<uint32_t> node;
+  GenArr<int> last, len;
+};
+__device__ __forceinline__ PrefixView prefix_view(const Prefix& z, int g, int stride8, int stride4) {
+  const int o8 = g * stride8, o4 = g * stride4;
+  PrefixView v;
+  v.H = {z.H, o8}; v.Hpar = {z.Hpar, o8}; v.Hstrip = {z.Hstrip, o8}; v.hl = {z.hl, o8}; v.ho = {z.ho, o8};
+  v.sb = {z.sb, o8}; v.snb = {z.snb, o8};
+  v.node = {z.node, o4}; v.last = {z.last, o4}; v.len = {z.len, o4};
+  return v;
+}
 __device__ __forceinline__ Prefix prefix_at(unsigned char* p, int W) {
   Prefix a;
   a.H = (uint64_t*)carve(p, 8 * W);
@@ -171,11 +197,19 @@ __device__ __forceinline__ Prefix prefix_at(unsigned char* p, int W) {
   return a;
 }
 
-// slots of the per-frame history-key table (pow2, >= 2 * W when the scratch it overlays allows)
+// slots of the per-frame history-key table (pow2 >= 2 * W: load factor at most one half)
 __host__ __device__ inline int beam_hk_slots(int W, int NCAND) {
+  (void)NCAND;
   int n = 4;
-  while (n < 2 * W && 12 * (2 * n) <= 8 * NCAND) n <<= 1;
+  while (n < 2 * W) n <<= 1;
   return n;
+}
+
+// scratch shared by the bucket cut (bucket of each alive entry, boundary list: 2 x NCAND ints) and, after it, the
+// history-key table (key, best score, lowest index: 20 bytes per slot)
+__host__ __device__ inline size_t beam_scratch_bytes(int W, int NCAND) {
+  const size_t a = 8 * (size_t)NCAND, b = 20 * (size_t)beam_hk_slots(W, NCAND);
+  return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
 __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND) {
@@ -187,8 +221,8 @@ __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, 
   s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
   s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // candidate score, desc
   s += al(4 * (size_t)NCAND);                               // alive idx
-  s += 2 * al(4 * (size_t)NCAND) + al(4 * 256);             // bucket of each alive entry, boundary list (also: history-key table), histogram
-  s += al(8 * (size_t)(W + 1)) + al(4 * (size_t)(W + 1));   // the W survivors of the bucket cut
+  s += beam_scratch_bytes(W, NCAND) + al(4 * 256);          // bucket cut scratch / history-key table, histogram
+  s += al(4 * (size_t)(W + 1));                             // the W survivors of the bucket cut
   s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
   s += al(8 * (size_t)(W + 1));                             // sel_hk
   s += 2 * (al(4 * (size_t)VL) + al(VL));                   // frame records: rl[VL], cs[VL] (x2)
@@ -286,23 +320,36 @@ __device__ void condition_frame(const float* __restrict__ row, const BeamParams&
     if (k < P.VL) fr.rl[k] = (x[i] >= tmin || k == best_k) ? x[i] : -INFINITY;
   }
   __syncwarp();
-  // order non-blank candidates by (log-prob desc, label asc) through rank counting
-  int cnt = 0;
+  // order non-blank candidates by (log-prob desc, label asc): rank = number of candidates ahead.  The loop runs over
+  // the CANDIDATES (set bits of a ballot, values handed round by shuffle) -- one or two for a confident frame --
+  // not over all VL labels.
+  const int ngrp = (P.VL + 31) >> 5;
+  bool cand[PER];
+  int rank[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int k = lane + 32 * i;
-    if (k >= 1 && k < P.VL && fr.rl[k] != -INFINITY) {
-      const float mine = fr.rl[k];
-      int rank = 0;
-      for (int q = 1; q < P.VL; ++q) {
-        const float o = fr.rl[q];
-        rank += (o > mine || (o == mine && q < k)) ? 1 : 0;  // -inf never outranks a candidate
-      }
-      fr.cs[rank] = (unsigned char)k;
-      ++cnt;
+    cand[i] = k >= 1 && k < P.VL && (x[i] >= tmin || k == best_k);
+    rank[i] = 0;
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int g = 0; g < PER; ++g) {
+    if (g >= ngrp) break;  // warp-uniform
+    unsigned m = __ballot_sync(FULL, cand[g]);
+    cnt += __popc(m);
+    while (m) {
+      const int b = __ffs((int)m) - 1;
+      m &= m - 1u;
+      const float o = __shfl_sync(FULL, x[g], b);
+      const int q = b + 32 * g;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) rank[i] += (o > x[i] || (o == x[i] && q < lane + 32 * i)) ? 1 : 0;
     }
   }
-  cnt = __reduce_add_sync(FULL, cnt);
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    if (cand[i]) fr.cs[rank[i]] = (unsigned char)(lane + 32 * i);
   if (lane == 0) *nc1_out = cnt;
   __syncwarp();
 }
@@ -338,7 +385,9 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
 
   const int WC = P.W;  // capacity: every table below is sized for the widest setting of the launch
   unsigned char* const gen_base = sp;
-  const size_t gen_stride = prefix_gen_bytes(WC);
+  const size_t gen_stride = prefix_gen_bytes(WC);  // a multiple of 16
+  const Prefix gen0 = prefix_at(gen_base, WC);
+  const int gs8 = (int)(gen_stride / 8), gs4 = (int)(gen_stride / 4);
   sp += 2 * gen_stride;
   double* tot = (double*)carve(sp, 8 * WC);
   double* newb = (double*)carve(sp, 8 * WC);
@@ -353,10 +402,9 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
   double* cscore = (double*)carve(sp, 8 * NCAND);
   uint32_t* cdesc = (uint32_t*)carve(sp, 4 * NCAND);
   int* aidx = (int*)carve(sp, 4 * NCAND);
-  int* abkt = (int*)carve(sp, 4 * NCAND);   // abkt and blist are contiguous: after the cut they hold the history-key table
-  int* blist = (int*)carve(sp, 4 * NCAND);
+  int* abkt = (int*)carve(sp, beam_scratch_bytes(WC, NCAND));  // after the cut this scratch holds the history-key table
+  int* blist = abkt + NCAND;
   int* hist = (int*)carve(sp, 4 * 256);
-  double* bscore = (double*)carve(sp, 8 * (WC + 1));
   int* bidx = (int*)carve(sp, 4 * (WC + 1));
   int* sel = (int*)carve(sp, 4 * (WC + 1));
   int* sel_keep = (int*)carve(sp, 4 * (WC + 1));
@@ -382,7 +430,8 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
   // history-key table over the (by then free) abkt/blist scratch: keys, then the best rank per key
   const int HKS = beam_hk_slots(WC, NCAND);
   unsigned long long* hk_keys = reinterpret_cast<unsigned long long*>(abkt);
-  int* hk_rank = reinterpret_cast<int*>(hk_keys + HKS);
+  unsigned long long* hk_best = hk_keys + HKS;
+  int* hk_idx = reinterpret_cast<int*>(hk_best + HKS);
 
   const int tid = (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -427,7 +476,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
 
     // ---------------- initial beam: the empty prefix, blank-ended with score 0
     if (tid == 0) {
-      const Prefix a = prefix_at(gen_base, WC);
+      const Prefix& a = gen0;
       a.H[0] = hmix(0x243F6A8885A308D3ull, 0u);
       a.Hpar[0] = 0ull;  // never a key
       a.Hstrip[0] = a.H[0];
@@ -444,7 +493,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
     }
     for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
     __syncthreads();
-    if (tid == 0) table_insert(tkeys, tvals, tmask, prefix_at(gen_base, WC).H[0], 0);
+    if (tid == 0) table_insert(tkeys, tvals, tmask, gen0.H[0], 0);
 
     // ---------------- producer prologue: chunk 0 (+1 in flight), frame 0 record
     auto load_chunk = [&](int c) {  // producer warp
@@ -497,8 +546,8 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
         continue;
       }
       // ============================ consumers ============================
-      const Prefix A = prefix_at(gen_base + g * gen_stride, WC);
-      const Prefix N = prefix_at(gen_base + (g ^ 1) * gen_stride, WC);
+      const PrefixView A = prefix_view(gen0, g, gs8, gs4);
+      const PrefixView N = prefix_view(gen0, g ^ 1, gs8, gs4);
       const FrameRec F = frame_rec(t);
       const int nc1 = sc->nc1[t & 1];
       const int np = sc->np;
@@ -553,14 +602,20 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
       }
       cons_sync();
 
-      // ---- phase 2: rank by tot; per-prefix entries
+      // ---- phase 2: rank by tot; per-prefix entries.  The rank only sets the staircase width of a row; when even the
+      // last row keeps all nc1 candidates (few candidates: every frame of a confident model) no row is cut and the
+      // prefixes keep their order.
       const float r_blank = F.rl[0];
+      const bool cut_rows = nc1 > W / np + 1;
       for (int p = tid; p < np; p += BM_CONS) {
         const double mine = tot[p];
-        int rk = 0;
-        for (int q = 0; q < np; ++q) {
-          const double o = tot[q];
-          rk += (o > mine || (o == mine && q < p)) ? 1 : 0;
+        int rk = p;
+        if (cut_rows) {
+          rk = 0;
+          for (int q = 0; q < np; ++q) {
+            const double o = tot[q];
+            rk += (o > mine || (o == mine && q < p)) ? 1 : 0;
+          }
         }
         rank2p[rk] = p;
         const int e = A.last[p];
@@ -670,10 +725,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
           if (alive) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
             aidx[pos] = k;
-            if (pos <= W) {  // at most W alive (the usual case): this already is the list that gets ranked
-              bscore[pos] = cscore[k];
-              bidx[pos] = k;
-            }
+            if (pos < W) sel[pos] = k;  // at most W alive (the usual case): this already is the selection
           }
           running += totc;
           cons_sync();
@@ -688,7 +740,8 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
       // over [cutoff, max] -- everything in buckets above the boundary bucket is in, the boundary
       // bucket is resolved by exact rank among its few members -- then rank only those W.
       // Same ordering rule as a full rank count (score desc, candidate index asc), so same result.
-      int n_rank = n_alive;  // entries to rank: (bscore[i], bidx[i]), i < n_rank
+      // (At most W alive: all of them are selected, in candidate order -- the order of the selection only decides
+      // slot and node numbers, and the best entry per history key is found by score below, not by rank.)
       if (n_alive > W) {
         for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
@@ -757,7 +810,6 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
             }
             if (in) {
               const int pos = off + __popc(mk & ((1u << lane) - 1u));
-              bscore[pos] = cscore[aidx[i]];
               bidx[pos] = aidx[i];
             }
             running += totc;
@@ -765,16 +817,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
           }
           SSD_ASSERT(running == W);
         }
-        n_rank = W;
-      }
-      for (int i = tid; i < n_rank; i += BM_CONS) {
-        const double mine = bscore[i];
-        int rk = 0;
-        for (int j = 0; j < n_rank; ++j) {
-          const double o = bscore[j];
-          rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
-        }
-        if (rk < W) sel[rk] = bidx[i];
+        for (int i = tid; i < W; i += BM_CONS) sel[i] = bidx[i];
       }
       cons_sync();
 
@@ -795,12 +838,14 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
         sel_hk[r] = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);
       }
       for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
-      // best rank per history key through a small hash table (over scratch the cut above no longer needs): an entry
-      // survives iff it holds the best rank of its key.  Replaces a scan of every better-ranked entry (16 % of the
-      // kernel's instructions at config 3).
+      // Best entry per history key through a small hash table (over scratch the cut above no longer needs): highest
+      // score, and among equal scores the lowest candidate index -- what "first in rank order" means -- found with
+      // one atomicMax and one atomicMin per entry.  Replaces a full ranking of the selection followed by a scan of
+      // every better-ranked entry (a quarter of the kernel's instructions at config 3).
       for (int i = tid; i < HKS; i += BM_CONS) {
         hk_keys[i] = 0ull;
-        hk_rank[i] = 0x7fffffff;
+        hk_best[i] = 0ull;
+        hk_idx[i] = 0x7fffffff;
       }
       cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
@@ -811,12 +856,17 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
           if (old == 0ull || old == hk) break;
           s_ = (s_ + 1) & (HKS - 1);
         }
-        atomicMin(&hk_rank[s_], r);
-        sel_slot[r] = s_;  // remembered for the read-back below (sel_slot is rewritten in phase 6a)
+        atomicMax(&hk_best[s_], order_key(cscore[sel[r]]));
+        sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
       }
       cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
-        int keep = hk_rank[sel_slot[r]] == r ? 1 : 0;
+        const int s_ = sel_slot[r];
+        if (order_key(cscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
+      }
+      cons_sync();
+      for (int r = tid; r < n_sel; r += BM_CONS) {
+        int keep = hk_idx[sel_slot[r]] == sel[r] ? 1 : 0;
         const uint32_t d = cdesc[sel[r]];
         const int c = (int)(d & 0xFFu);
         if (keep && (c == 0 || c == 0xFE)) {
@@ -898,7 +948,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
     // ---------------- finish: merge variants, pick the best text, emit labels
     __syncthreads();
     if (!producer) {
-      const Prefix A = prefix_at(gen_base + g * gen_stride, WC);
+      const PrefixView A = prefix_view(gen0, g, gs8, gs4);
       const int np = sc->np;
       for (int p = tid; p < np; p += BM_CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
       cons_sync();

@@ -85,6 +85,9 @@ constexpr int F_NRAW = SSD_F_NRAW;  // raw-row ring depth per main
 #ifndef SSD_F_PFD
 #define SSD_F_PFD 0  // L2 prefetch distance of the loaders, in blocks (0 = off: no gain measured, warm or cold)
 #endif
+#ifndef SSD_F_L2HINT
+#define SSD_F_L2HINT 1  // L2 eviction priorities on the bulk copies of the log-prob rows (keep for re-reads, drop after the last)
+#endif
 #ifndef SSD_F_LDSLEEP
 #define SSD_F_LDSLEEP 2000u  // ns between a loader's polls of its ring's empty barrier; 0 = hardware-suspended try_wait
 #endif
@@ -684,7 +687,9 @@ __device__ void fast_loader(const FastParams& P, const MainView& mv, const FPlan
     const int slot = (int)((qbase + (unsigned)bi) % F_NRAW);
     const uint32_t bytes = (uint32_t)(n * V * 4);
     mbar_arrive_expect_tx(&mv.bar[FB_RAW + slot], bytes + (lse_base ? F_K * 4u : 0u));
-    bulk_g2s(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot]);
+    // the sweeps' reads are the first two of three: ask L2 to keep the lines for the block workers
+    if (SSD_F_L2HINT) bulk_g2s_hint(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot], 1);
+    else bulk_g2s(mv.raw(slot), base + (int64_t)q * F_K * P.st, bytes, &mv.bar[FB_RAW + slot]);
     if (lse_base) bulk_g2s(mv.raw(slot) + F_K * V, lse_base + q * F_K, F_K * 4u, &mv.bar[FB_RAW + slot]);
   };
   // The rows come from HBM the first time (~1.5 us per bulk copy, measured: with F_NRAW - 1 = 2 copies in flight the
@@ -832,7 +837,9 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
     const int n = min(F_K, pl.Tb - q * F_K);
     const uint32_t bytes = (uint32_t)(n * V * 4);
     mbar_arrive_expect_tx(&wv.rawbar[use & 1u], bytes + (lse_base ? F_K * 4u : 0u));
-    bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
+    // the workers are the last readers of a block's rows
+    if (SSD_F_L2HINT) bulk_g2s_hint(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u], 0);
+    else bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride, lp_base + (int64_t)q * F_K * P.st, bytes, &wv.rawbar[use & 1u]);
     if (lse_base) bulk_g2s(wv.raw0 + (use & 1u) * wv.raw_stride + F_K * V, lse_base + q * F_K, F_K * 4u, &wv.rawbar[use & 1u]);
   };
   if (!late) bar_sync(1, 32 * (F_W + 2));  // released by the two mains shortly before the first block can be ready

@@ -133,6 +133,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 #endif
 }
+// The same copy with an L2 eviction priority for the lines it touches (cp.async.bulk ... .L2::cache_hint):
+// keep = 1: evict_last, the data will be read again by this kernel (the loss reads every log-prob three times: both
+// sweeps and the block workers); keep = 0: evict_first, this was the last reader.
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, int keep) {
+#ifdef SSD_EMU
+  (void)keep;
+  emu::bulk_g2s(dst_smem, src_gmem, bytes, bar);
+#else
+  uint64_t pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+#endif
+}
 // Hint: pull `bytes` (multiple of 16) at `src_gmem` into L2 ahead of the bulk copy that will fetch them
 // (cp.async.bulk.prefetch.L2, SASS UBLKPF).  No shared memory, no completion to wait for.
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
