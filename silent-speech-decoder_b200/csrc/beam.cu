@@ -842,31 +842,48 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
       // score, and among equal scores the lowest candidate index -- what "first in rank order" means -- found with
       // one atomicMax and one atomicMin per entry.  Replaces a full ranking of the selection followed by a scan of
       // every better-ranked entry (a quarter of the kernel's instructions at config 3).
-      for (int i = tid; i < HKS; i += BM_CONS) {
-        hk_keys[i] = 0ull;
-        hk_best[i] = 0ull;
-        hk_idx[i] = 0x7fffffff;
-      }
-      cons_sync();
-      for (int r = tid; r < n_sel; r += BM_CONS) {
-        const unsigned long long hk = (unsigned long long)sel_hk[r];  // never 0 (hmix)
-        int s_ = (int)(hk & (unsigned long long)(HKS - 1));
-        for (;;) {
-          const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, hk);
-          if (old == 0ull || old == hk) break;
-          s_ = (s_ + 1) & (HKS - 1);
+      const bool small_sel = n_sel <= 24;  // a handful of entries (narrow beams, confident frames): compare directly, one phase
+      if (!small_sel) {
+        for (int i = tid; i < HKS; i += BM_CONS) {
+          hk_keys[i] = 0ull;
+          hk_best[i] = 0ull;
+          hk_idx[i] = 0x7fffffff;
         }
-        atomicMax(&hk_best[s_], order_key(cscore[sel[r]]));
-        sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
+        cons_sync();
+        for (int r = tid; r < n_sel; r += BM_CONS) {
+          const unsigned long long hk = (unsigned long long)sel_hk[r];  // never 0 (hmix)
+          int s_ = (int)(hk & (unsigned long long)(HKS - 1));
+          for (;;) {
+            const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, hk);
+            if (old == 0ull || old == hk) break;
+            s_ = (s_ + 1) & (HKS - 1);
+          }
+          atomicMax(&hk_best[s_], order_key(cscore[sel[r]]));
+          sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
+        }
+        cons_sync();
+        for (int r = tid; r < n_sel; r += BM_CONS) {
+          const int s_ = sel_slot[r];
+          if (order_key(cscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
+        }
+        cons_sync();
+      } else {
+        cons_sync();  // sel_hk and keepf are visible
       }
-      cons_sync();
       for (int r = tid; r < n_sel; r += BM_CONS) {
-        const int s_ = sel_slot[r];
-        if (order_key(cscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
-      }
-      cons_sync();
-      for (int r = tid; r < n_sel; r += BM_CONS) {
-        int keep = hk_idx[sel_slot[r]] == sel[r] ? 1 : 0;
+        int keep;
+        if (small_sel) {
+          const uint64_t hk = sel_hk[r];
+          const double mine = cscore[sel[r]];
+          keep = 1;
+          for (int q = 0; q < n_sel; ++q) {
+            if (q == r || sel_hk[q] != hk) continue;
+            const double o = cscore[sel[q]];
+            if (o > mine || (o == mine && sel[q] < sel[r])) keep = 0;
+          }
+        } else {
+          keep = hk_idx[sel_slot[r]] == sel[r] ? 1 : 0;
+        }
         const uint32_t d = cdesc[sel[r]];
         const int c = (int)(d & 0xFFu);
         if (keep && (c == 0 || c == 0xFE)) {
