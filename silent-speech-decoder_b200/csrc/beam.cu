@@ -35,6 +35,7 @@
 //   6  compact survivors into the next prefix table, append back-pointer nodes, rebuild hash table
 // End: merge blank-/char-ending and trailing-space variants, arg-max, walk back-pointers.
 #include <cmath>
+#include <cstdlib>
 
 #include "ssd_common.cuh"
 
@@ -64,6 +65,7 @@ struct BeamParams {
   int set_w[SSD_MAX_BEAM_SETTINGS];
   float set_bias[SSD_MAX_BEAM_SETTINGS], set_prune[SSD_MAX_BEAM_SETTINGS], set_tmin[SSD_MAX_BEAM_SETTINGS];
   int W;
+  int small_sel;  // selections up to this size take the direct history dedup (tuning knob SSD_BEAM_SMALL)
   int32_t* out_tok;
   int32_t* out_len;
   double* out_score;
@@ -114,7 +116,9 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
   const long long b = __double_as_longlong(v);
   return b >= 0 ? (unsigned long long)b ^ 0x8000000000000000ull : ~(unsigned long long)b;
 }
-// fp64 logaddexp in upstream's form: hi + log(1 + exp(lo - hi))
+// fp64 logaddexp in upstream's form: hi + log(1 + exp(lo - hi)).  Inlined on purpose: one shared out-of-line copy
+// (the fp64 log and exp are ~180 SASS instructions, four copies) cut the registers from 80 to 63 but measured 5 %
+// slower at 8 CTAs per SM (185k against 194k utterances/s on config 3, confident input).
 __device__ __forceinline__ double lse2(double a, double b) {
   const double hi = a >= b ? a : b, lo = a >= b ? b : a;
   if (lo == -INFINITY) return hi;
@@ -377,6 +381,17 @@ __device__ __forceinline__ int table_find(const unsigned long long* keys, const 
   }
 }
 
+// rows that a bulk copy cannot take (non-contiguous or unaligned input): a plain coalesced copy by the producer warp.
+// Out of line: it is cold code that was instantiated three times inside the hot kernel.
+__device__ __noinline__ void load_rows_strided(float* __restrict__ dst, const float* __restrict__ src, int rows, int V, int64_t st) {
+  const int lane = lane_id();
+  for (int i = lane; i < rows * V; i += 32) {
+    const int r = i / V, v = i - r * V;
+    dst[i] = ld_stream(src + (int64_t)r * st + v);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
@@ -507,11 +522,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
           bulk_g2s(dst, src, bytes, &sc->bar[c & 1]);
         }
       } else {
-        for (int i = lane; i < rows * P.V; i += 32) {
-          const int r = i / P.V, v = i - r * P.V;
-          dst[i] = ld_stream(src + (int64_t)r * P.st + v);
-        }
-        __syncwarp();
+        load_rows_strided(dst, src, rows, P.V, P.st);
       }
     };
     auto wait_chunk = [&](int c) {
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P)
       // score, and among equal scores the lowest candidate index -- what "first in rank order" means -- found with
       // one atomicMax and one atomicMin per entry.  Replaces a full ranking of the selection followed by a scan of
       // every better-ranked entry (a quarter of the kernel's instructions at config 3).
-      const bool small_sel = n_sel <= 24;  // a handful of entries (narrow beams, confident frames): compare directly, one phase
+      const bool small_sel = n_sel <= P.small_sel;  // a handful of entries (narrow beams, confident frames): compare directly, one phase
       if (!small_sel) {
         for (int i = tid; i < HKS; i += BM_CONS) {
           hk_keys[i] = 0ull;
@@ -1074,6 +1085,10 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
     width = settings[i].beam_width > width ? settings[i].beam_width : width;
   }
   P.W = width;
+  {
+    const char* e = std::getenv("SSD_BEAM_SMALL");
+    P.small_sel = e && *e ? std::atoi(e) : 8;  // measured: 24 costs 4 % on config 3, 0 costs 10 % at width 1
+  }
   P.out_tok = out_tok; P.out_len = out_len; P.out_score = out_score;
   P.VL = beam_vl(V, blank, P.pad);
   P.TS = beam_table_slots(width);
