@@ -41,12 +41,21 @@
 
 namespace ssd {
 
+#ifndef SSD_BEAM_CHUNK
+#define SSD_BEAM_CHUNK 8
+#endif
+#ifndef SSD_BEAM_TSMUL
+#define SSD_BEAM_TSMUL 4  // hash table slots per beam entry (pow2 above it)
+#endif
+#ifndef SSD_BEAM_MINCTAS
+#define SSD_BEAM_MINCTAS 8
+#endif
 #ifndef SSD_BEAM_CONS
 #define SSD_BEAM_CONS 64
 #endif
 constexpr int BM_CONS = SSD_BEAM_CONS;    // consumer threads (a per-frame phase rarely has more than ~100 items)
 constexpr int BM_THREADS = BM_CONS + 32;  // + producer warp
-constexpr int BM_CHUNK = 8;              // frames per TMA chunk (two buffers; shared memory decides the CTAs per SM)
+constexpr int BM_CHUNK = SSD_BEAM_CHUNK;              // frames per TMA chunk (two buffers; shared memory decides the CTAs per SM)
 constexpr int BAR_CONS = 1;              // named barrier: consumers only
 constexpr int BAR_FRAME = 2;             // named barrier: consumers + producer, once per frame
 constexpr int LBL_NONE = 255;
@@ -90,7 +99,7 @@ __host__ __device__ inline int beam_ncand_cap(int W, int VL) {
 }
 __host__ __device__ inline int beam_table_slots(int W) {
   int ts = 64;
-  while (ts < 4 * W) ts <<= 1;
+  while (ts < SSD_BEAM_TSMUL * W) ts <<= 1;
   return ts;
 }
 
@@ -393,7 +402,7 @@ __device__ __noinline__ void load_rows_strided(float* __restrict__ dst, const fl
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(BM_THREADS, 8) beam_kernel(const BeamParams P) {
+__global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
   const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
