@@ -549,7 +549,14 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
     __syncthreads();
 
     int g = 0;  // current prefix generation
+#ifdef SSD_BEAM_PROF
+    long long pf_prod = 0, pf_fast = 0, pf_gen = 0, pf_wait = 0;
+    int pf_nfast = 0, pf_ngen = 0;
+#endif
     for (int t = 0; t < len; ++t) {
+#ifdef SSD_BEAM_PROF
+      const long long pf_t0 = clock64();
+#endif
       if (producer) {
         // -------- condition frame t+1 while the consumers work on frame t
         const int tn = t + 1;
@@ -562,7 +569,16 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
           }
           condition_frame(chunk_buf(c) + r * P.V, P, s_bias, s_tmin, lab2voc, frame_rec(tn), &sc->nc1[tn & 1]);
         }
+#ifdef SSD_BEAM_PROF
+        const long long pf_t1 = clock64();
+        pf_prod += pf_t1 - pf_t0;
+#endif
         bar_sync(BAR_FRAME, BM_THREADS);
+#ifdef SSD_BEAM_PROF
+        pf_wait += clock64() - pf_t1;
+        if (t == len - 1 && blockIdx.x == 0 && lane == 0)
+          printf("producer: %d frames, busy %lld cycles/frame, waiting %lld cycles/frame\n", len, pf_prod / len, pf_wait / len);
+#endif
         continue;
       }
       // ============================ consumers ============================
@@ -579,14 +595,32 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       // does not change.  If none falls below the relative cut and no two share a history key, the general path
       // would copy every prefix to the same slot of the next generation: update the scores in place instead and
       // leave the hash table alone.  Otherwise (rare) the general path below does the frame.
-      if (nc1 == 0 && F.rl[0] != -INFINITY) {
-        const double rb = (double)F.rl[0];
+      const bool blank_only = nc1 == 0 && F.rl[0] != -INFINITY;
+      // ---- repeat-only frame: the candidate set is one label c, blank is not in it (the 2nd, 3rd, .. frame of a
+      // confidently emitted label).  If every live prefix ends in c and none has blank-ended mass (the previous frame
+      // had no blank candidate either), the general path gives every prefix exactly its char-ended entry back, scored
+      // snb + r_c: the blank entry is -inf, the extension P+c needs blank-ended mass and is -inf, the parent's
+      // contribution is the parent's blank-ended mass and is -inf, and lse2(x, -inf) = x.  Same in-place update.
+      const bool repeat_cand = nc1 == 1 && F.rl[0] == -INFINITY;
+      if (blank_only || repeat_cand) {
+        const int c1 = repeat_cand ? (int)F.cs[0] : 0;
+        const double rb = (double)F.rl[c1];
         double m = neg_inf();
+        bool general = false;
         for (int p = tid; p < np; p += BM_CONS) {
-          const double v = lse2(A.sb[p], A.snb[p]) + rb;
+          double v;
+          uint32_t lc;
+          if (blank_only) {
+            v = lse2(A.sb[p], A.snb[p]) + rb;
+            lc = 0u;
+          } else {
+            if (A.last[p] != c1 || A.sb[p] != -INFINITY) general = true;
+            v = A.snb[p] + rb;
+            lc = (uint32_t)c1;
+          }
           newb[p] = v;
           m = v > m ? v : m;
-          sel_hk[p] = hmix(hmix(A.hl[p] ^ hmix(A.ho[p], 0x5bu), 0xa7u), 0x100u);  // phase 5's key with last char = blank
+          sel_hk[p] = hmix(hmix(A.hl[p] ^ hmix(A.ho[p], 0x5bu), 0xa7u), 0x100u + lc);  // phase 5's key of that entry
         }
         m = warp_max_d(m);
         if (lane == 0) sc->wmax[warp] = m;
@@ -595,7 +629,6 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         double mm = sc->wmax[0];
         for (int w = 1; w < BM_CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
         const double cut = mm + (double)s_prune;
-        bool general = false;
         for (int p = tid; p < np; p += BM_CONS) {
           const double v = newb[p];
           if (!(v >= cut) || v == -INFINITY) general = true;
@@ -607,10 +640,22 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         cons_sync();
         if (sc->n_b == 0) {
           for (int p = tid; p < np; p += BM_CONS) {
-            A.sb[p] = newb[p];
-            A.snb[p] = neg_inf();
+            if (blank_only) {
+              A.sb[p] = newb[p];
+              A.snb[p] = neg_inf();
+            } else {
+              A.snb[p] = newb[p];
+            }
           }
+#ifdef SSD_BEAM_PROF
+          const long long pf_t1 = clock64();
+          pf_fast += pf_t1 - pf_t0;
+          ++pf_nfast;
+#endif
           bar_sync(BAR_FRAME, BM_THREADS);  // same generation, same table; frame t+1's record is visible
+#ifdef SSD_BEAM_PROF
+          pf_wait += clock64() - pf_t1;
+#endif
           continue;
         }
       }
@@ -979,8 +1024,21 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         sc->nodes_used = node0 + (unsigned)n_new;
       }
       g ^= 1;
+#ifdef SSD_BEAM_PROF
+      const long long pf_t1 = clock64();
+      pf_gen += pf_t1 - pf_t0;
+      ++pf_ngen;
+#endif
       bar_sync(BAR_FRAME, BM_THREADS);  // next generation, table, and frame t+1 record are all visible
+#ifdef SSD_BEAM_PROF
+      pf_wait += clock64() - pf_t1;
+#endif
     }
+#ifdef SSD_BEAM_PROF
+    if (!producer && blockIdx.x == 0 && tid == 0)
+      printf("consumers: %d fast frames at %lld cycles, %d general frames at %lld cycles, waiting %lld cycles/frame\n", pf_nfast,
+             pf_nfast ? pf_fast / pf_nfast : 0, pf_ngen, pf_ngen ? pf_gen / pf_ngen : 0, len ? pf_wait / len : 0);
+#endif
 
     // ---------------- finish: merge variants, pick the best text, emit labels
     __syncthreads();

@@ -11,6 +11,7 @@ The distillation term is small dense PyTorch work and stays PyTorch (north_star)
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -103,8 +104,21 @@ class _CTCFused(torch.autograd.Function):
         return out, None, None, None, None, None, None, None, None
 
 
+def _check_device_lengths(input_lengths, target_lengths, T: int, S_max) -> None:
+    """Opt-in (``validate_lengths=True`` or ``SSD_VALIDATE_LENGTHS=1``): torch raises on out-of-range lengths; the
+    kernels do not read device-resident lengths back (that would synchronise every step) and turn such a row into
+    NaN instead.  This check costs that synchronisation and restores the exception."""
+    bad_in = ((input_lengths < 0) | (input_lengths > T)).any()
+    bad_tg = (target_lengths < 0).any() if S_max is None else ((target_lengths < 0) | (target_lengths > S_max)).any()
+    if bool(bad_in):
+        raise RuntimeError(f"Expected input_lengths to have value in [0, {T}] (the time dimension of log_probs)")
+    if bool(bad_tg):
+        raise RuntimeError("Expected target_lengths to have value in [0, the width of targets]")
+
+
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank: int = 0, reduction: str = "mean",
-             zero_infinity: bool = False, from_logits: bool = False, expect_grad: float = 1.0) -> torch.Tensor:
+             zero_infinity: bool = False, from_logits: bool = False, expect_grad: float = 1.0,
+             validate_lengths: bool = False) -> torch.Tensor:
     """``torch.nn.functional.ctc_loss`` semantics on the native kernel.  log_probs: (T,B,V).
 
     ``from_logits`` (scope row f-2): the input is the CTC head's pre-softmax output (``heads.py:36``); the result is
@@ -134,6 +148,8 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank: int = 0, 
     _check_host_lengths("input_lengths", input_lengths, T, "the time dimension of log_probs")
     if targets.dim() == 2:
         _check_host_lengths("target_lengths", target_lengths, targets.size(1), "the width of targets")
+    if (validate_lengths or os.environ.get("SSD_VALIDATE_LENGTHS") == "1") and (input_lengths.is_cuda or target_lengths.is_cuda):
+        _check_device_lengths(input_lengths, target_lengths, T, targets.size(1) if targets.dim() == 2 else None)
     out = _CTCFused.apply(log_probs, targets, input_lengths, target_lengths, int(blank), bool(zero_infinity), reduction,
                           bool(from_logits), float(expect_grad))
     if reduction == "none" and unbatched:

@@ -378,3 +378,19 @@ def test_per_utterance_strip_widths(monkeypatch):
     # the default for this batch (900 > 4 x 148) is the per-width scheme: same bits as forcing it
     nll, gr = ops.ctc_loss_fwd_bwd(lp, il, tg, tl, blank=1, mean_denominator=B)
     assert torch.equal(nll, outs[("1", B)][0]) and torch.equal(gr, outs[("1", B)][1])
+
+
+def test_device_resident_bad_lengths(monkeypatch):
+    """Lengths that live on the device are not read back by default (no synchronisation on the training step): a bad
+    row comes back as NaN.  With validate_lengths=True (or SSD_VALIDATE_LENGTHS=1) the reference's RuntimeError is back."""
+    B, T = 3, 30
+    lp = synth.flat(B, T, 5).cuda().transpose(0, 1)
+    tg, tl = synth.targets(B, 6, 6)
+    il = torch.tensor([30, 31, 30]).cuda()   # 31 > T
+    out = ctc_loss(lp, tg.cuda(), il, tl.cuda(), blank=1, reduction="none", zero_infinity=True)
+    assert torch.isfinite(out[0]) and torch.isfinite(out[2])
+    with pytest.raises(RuntimeError):
+        ctc_loss(lp, tg.cuda(), il, tl.cuda(), blank=1, reduction="none", zero_infinity=True, validate_lengths=True)
+    monkeypatch.setenv("SSD_VALIDATE_LENGTHS", "1")
+    with pytest.raises(RuntimeError):
+        CTCLoss(blank=1)(lp, tg.cuda(), il, tl.cuda())
