@@ -516,6 +516,12 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       nodes[0] = make_uint2(0u, 0u);
     }
     for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
+    for (int i = tid; i < HKS; i += BM_THREADS) {
+      hk_keys[i] = 0ull;
+      hk_best[i] = 0ull;
+      hk_idx[i] = 0x7fffffff;
+    }
+    bool hk_dirty = false;
     __syncthreads();
     if (tid == 0) table_insert(tkeys, tvals, tmask, gen0.H[0], 0);
 
@@ -552,6 +558,11 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
 #ifdef SSD_BEAM_PROF
     long long pf_prod = 0, pf_fast = 0, pf_gen = 0, pf_wait = 0;
     int pf_nfast = 0, pf_ngen = 0;
+    long long pf_ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long pf_last = 0;
+#define PF_STAMP(k) do { const long long pf_now = clock64(); pf_ph[k] += pf_now - pf_last; pf_last = pf_now; } while (0)
+#else
+#define PF_STAMP(k) do { } while (0)
 #endif
     for (int t = 0; t < len; ++t) {
 #ifdef SSD_BEAM_PROF
@@ -660,6 +671,9 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         }
       }
 
+#ifdef SSD_BEAM_PROF
+      pf_last = clock64();
+#endif
       // ---- phase 1: tot, parent slot
       for (int p = tid; p < np; p += BM_CONS) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
@@ -667,6 +681,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       }
       cons_sync();
 
+      PF_STAMP(0);
       // ---- phase 2: rank by tot; per-prefix entries.  The rank only sets the staircase width of a row; when even the
       // last row keeps all nc1 candidates (few candidates: every frame of a confident model) no row is cut and the
       // prefixes keep their order.
@@ -694,13 +709,15 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
           if (pp >= 0) ext = ((A.last[pp] != e) ? tot[pp] : A.sb[pp]) + (double)r_e;
         }
         newnb[p] = lse2(rep, ext);
-        // staircase width of this row
+        // staircase width of this row (no row cut: every row holds nc1 proposals, its offset is known without a scan)
         int J = W / (rk + 1) + 1;
-        rowoff[rk] = J < nc1 ? J : nc1;
+        rowoff[rk] = cut_rows ? (J < nc1 ? J : nc1) : rk * nc1;
       }
       cons_sync();
 
-      // ---- phase 2b: exclusive scan of row widths (warp 0)
+      PF_STAMP(1);
+      // ---- phase 2b: exclusive scan of row widths (warp 0), only if some row is cut
+      if (cut_rows) {
       if (warp == 0) {
         int carry = 0;
         for (int i0 = 0; i0 < np; i0 += 32) {
@@ -718,11 +735,14 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         if (lane == 0) sc->n_e3 = carry;
       }
       cons_sync();
+      }
 
-      // ---- phase 3: candidate entries
-      const int n_e3 = sc->n_e3;
+      PF_STAMP(2);
+      // ---- phase 3: candidate entries (and, on the way, their maximum: phase 4a)
+      const int n_e3 = cut_rows ? sc->n_e3 : np * nc1;
       const int ncand = 2 * np + n_e3;
       SSD_ASSERT(ncand <= NCAND);
+      double m_loc = neg_inf();
       for (int k = tid; k < ncand; k += BM_CONS) {
         double s;
         uint32_t d;
@@ -753,23 +773,21 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         }
         cscore[k] = s;
         cdesc[k] = d;
+        m_loc = s > m_loc ? s : m_loc;
       }
+      m_loc = warp_max_d(m_loc);
+      if (lane == 0) sc->wmax[warp] = m_loc;
       cons_sync();
 
-      // ---- phase 4a: block max
-      {
-        double m = neg_inf();
-        for (int k = tid; k < ncand; k += BM_CONS) m = cscore[k] > m ? cscore[k] : m;
-        m = warp_max_d(m);
-        if (lane == 0) sc->wmax[warp] = m;
-      }
-      cons_sync();
+      PF_STAMP(3);
+      // ---- phase 4a: block max (the warps' maxima were left in sc->wmax by phase 3)
       double cutoff;
       {
         double m = sc->wmax[0];
         for (int w = 1; w < BM_CONS / 32; ++w) m = sc->wmax[w] > m ? sc->wmax[w] : m;
         cutoff = m + (double)s_prune;
       }
+      PF_STAMP(4);
       // ---- phase 4b: compact entries that survive the relative prune (order preserved)
       {
         int base_k = 0;
@@ -800,6 +818,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       cons_sync();
       const int n_alive = sc->n_alive;
       const int n_sel = n_alive < W ? n_alive : W;
+      PF_STAMP(5);
       // ---- phase 4c: the W best alive entries go to sel[rank].
       // More than W alive (flat posteriors): first cut down to exactly W with a 256-bucket histogram
       // over [cutoff, max] -- everything in buckets above the boundary bucket is in, the boundary
@@ -808,6 +827,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       // (At most W alive: all of them are selected, in candidate order -- the order of the selection only decides
       // slot and node numbers, and the best entry per history key is found by score below, not by rank.)
       if (n_alive > W) {
+        hk_dirty = true;  // the bucket cut works in the memory the history-key table lives in
         for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
         cons_sync();
@@ -886,7 +906,23 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       }
       cons_sync();
 
-      // ---- phase 5: history keys, then keep the best entry per key
+      PF_STAMP(6);
+      // ---- phase 5: history keys, then keep the best entry per key.
+      // Best entry per key through a small hash table (over scratch the cut above no longer needs): highest score, and
+      // among equal scores the lowest candidate index -- what "first in rank order" means -- found with one atomicMax
+      // and one atomicMin per entry.  Replaces a full ranking of the selection followed by a scan of every
+      // better-ranked entry (a quarter of the kernel's instructions at config 3).  The table is kept ZEROED between
+      // uses (re-zeroed in phase 6a, and here only after the cut has used its memory), so the keys are inserted by
+      // the same loop that computes them: three barriers for the phase instead of five.
+      const bool small_sel = n_sel <= P.small_sel;  // a handful of entries (narrow beams): compare directly, one pass
+      if (hk_dirty && !small_sel) {
+        for (int i = tid; i < HKS; i += BM_CONS) {
+          hk_keys[i] = 0ull;
+          hk_best[i] = 0ull;
+          hk_idx[i] = 0x7fffffff;
+        }
+        cons_sync();
+      }
       for (int r = tid; r < n_sel; r += BM_CONS) {
         const uint32_t d = cdesc[sel[r]];
         const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
@@ -899,41 +935,28 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
           if (c == space_lbl) { hl = ho; ho = 0ull; }
           else ho = hmix(ho, (uint32_t)c);
         }
-        // one 64-bit key for (last word, open word, last char): the duplicate scan below then compares one value
-        sel_hk[r] = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);
-      }
-      for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
-      // Best entry per history key through a small hash table (over scratch the cut above no longer needs): highest
-      // score, and among equal scores the lowest candidate index -- what "first in rank order" means -- found with
-      // one atomicMax and one atomicMin per entry.  Replaces a full ranking of the selection followed by a scan of
-      // every better-ranked entry (a quarter of the kernel's instructions at config 3).
-      const bool small_sel = n_sel <= P.small_sel;  // a handful of entries (narrow beams, confident frames): compare directly, one phase
-      if (!small_sel) {
-        for (int i = tid; i < HKS; i += BM_CONS) {
-          hk_keys[i] = 0ull;
-          hk_best[i] = 0ull;
-          hk_idx[i] = 0x7fffffff;
-        }
-        cons_sync();
-        for (int r = tid; r < n_sel; r += BM_CONS) {
-          const unsigned long long hk = (unsigned long long)sel_hk[r];  // never 0 (hmix)
-          int s_ = (int)(hk & (unsigned long long)(HKS - 1));
+        // one 64-bit key for (last word, open word, last char)
+        const uint64_t hk = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);  // never 0 (hmix)
+        sel_hk[r] = hk;
+        if (!small_sel) {
+          int s_ = (int)(hk & (uint64_t)(HKS - 1));
           for (;;) {
-            const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, hk);
-            if (old == 0ull || old == hk) break;
+            const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, (unsigned long long)hk);
+            if (old == 0ull || old == (unsigned long long)hk) break;
             s_ = (s_ + 1) & (HKS - 1);
           }
           atomicMax(&hk_best[s_], order_key(cscore[sel[r]]));
           sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
         }
-        cons_sync();
+      }
+      for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
+      cons_sync();
+      if (!small_sel) {
         for (int r = tid; r < n_sel; r += BM_CONS) {
           const int s_ = sel_slot[r];
           if (order_key(cscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
         }
         cons_sync();
-      } else {
-        cons_sync();  // sel_hk and keepf are visible
       }
       for (int r = tid; r < n_sel; r += BM_CONS) {
         int keep;
@@ -961,6 +984,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       }
       cons_sync();
 
+      PF_STAMP(7);
       // ---- phase 6a: slots.  warp 0 scans surviving old prefixes, warp 1 the new ones.
       if (warp == 0) {
         int carry = 0;
@@ -985,8 +1009,17 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         if (lane == 0) sc->n_new = carry;
       }
       for (int i = tid; i < TS; i += BM_CONS) tkeys[i] = 0ull;
+      if (!small_sel) {  // the history-key table goes back to zero for its next use (its last read is behind the barrier above)
+        for (int i = tid; i < HKS; i += BM_CONS) {
+          hk_keys[i] = 0ull;
+          hk_best[i] = 0ull;
+          hk_idx[i] = 0x7fffffff;
+        }
+      }
+      hk_dirty = false;
       cons_sync();
 
+      PF_STAMP(8);
       // ---- phase 6b: write the next generation and its hash table
       const int n_old = sc->n_keep_old, n_new = sc->n_new;
       SSD_ASSERT(n_old + n_new >= 1 && n_old + n_new <= W);
@@ -1024,6 +1057,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         sc->nodes_used = node0 + (unsigned)n_new;
       }
       g ^= 1;
+      PF_STAMP(9);
 #ifdef SSD_BEAM_PROF
       const long long pf_t1 = clock64();
       pf_gen += pf_t1 - pf_t0;
@@ -1036,8 +1070,13 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
     }
 #ifdef SSD_BEAM_PROF
     if (!producer && blockIdx.x == 0 && tid == 0)
+    {
       printf("consumers: %d fast frames at %lld cycles, %d general frames at %lld cycles, waiting %lld cycles/frame\n", pf_nfast,
              pf_nfast ? pf_fast / pf_nfast : 0, pf_ngen, pf_ngen ? pf_gen / pf_ngen : 0, len ? pf_wait / len : 0);
+      const int n = pf_ngen ? pf_ngen : 1;
+      printf("  general frame by phase (cycles): 1 %lld | 2 %lld | 2b %lld | 3 %lld | 4a %lld | 4b %lld | 4c %lld | 5 %lld | 6a %lld | 6b %lld\n",
+             pf_ph[0] / n, pf_ph[1] / n, pf_ph[2] / n, pf_ph[3] / n, pf_ph[4] / n, pf_ph[5] / n, pf_ph[6] / n, pf_ph[7] / n, pf_ph[8] / n, pf_ph[9] / n);
+    }
 #endif
 
     // ---------------- finish: merge variants, pick the best text, emit labels
