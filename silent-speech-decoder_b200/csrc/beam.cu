@@ -674,19 +674,20 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
 #ifdef SSD_BEAM_PROF
       pf_last = clock64();
 #endif
-      // ---- phase 1: tot, parent slot
+      // ---- phase 1: tot, parent slot.  (When no staircase row is cut -- see phase 2 -- nobody needs another prefix's
+      // tot before phase 3 except for the parent's, which is then recomputed on the spot: phases 1 and 2 share a barrier.)
+      const bool cut_rows = nc1 > W / np + 1;
       for (int p = tid; p < np; p += BM_CONS) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
         par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
       }
-      cons_sync();
+      if (cut_rows) cons_sync();
 
       PF_STAMP(0);
       // ---- phase 2: rank by tot; per-prefix entries.  The rank only sets the staircase width of a row; when even the
       // last row keeps all nc1 candidates (few candidates: every frame of a confident model) no row is cut and the
       // prefixes keep their order.
       const float r_blank = F.rl[0];
-      const bool cut_rows = nc1 > W / np + 1;
       for (int p = tid; p < np; p += BM_CONS) {
         const double mine = tot[p];
         int rk = p;
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
           // repeat of the last char keeps the text; an absorbed space also collects the blank-ended mass
           rep = (e == space_lbl ? mine : A.snb[p]) + (double)r_e;
           const int pp = par[p];
-          if (pp >= 0) ext = ((A.last[pp] != e) ? tot[pp] : A.sb[pp]) + (double)r_e;
+          if (pp >= 0) ext = ((A.last[pp] != e) ? (cut_rows ? tot[pp] : lse2(A.sb[pp], A.snb[pp])) : A.sb[pp]) + (double)r_e;
         }
         newnb[p] = lse2(rep, ext);
         // staircase width of this row (no row cut: every row holds nc1 proposals, its offset is known without a scan)
@@ -789,10 +790,12 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       }
       PF_STAMP(4);
       // ---- phase 4b: compact entries that survive the relative prune (order preserved)
+      int n_alive;
       {
-        int base_k = 0;
+        // ballots over chunks of BM_CONS.  (One scan over per-thread runs of candidates -- two barriers however many
+        // candidates -- measured 4 % slower on config 3: the scan's five dependent shuffles cost more than the barriers.)
         int running = 0;
-        for (; base_k < ncand; base_k += BM_CONS) {
+        for (int base_k = 0; base_k < ncand; base_k += BM_CONS) {
           const int k = base_k + tid;
           const bool alive = k < ncand && cscore[k] >= cutoff && cscore[k] != -INFINITY;
           const unsigned m = __ballot_sync(FULL, alive);
@@ -808,15 +811,14 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
           if (alive) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
             aidx[pos] = k;
-            if (pos < W) sel[pos] = k;  // at most W alive (the usual case): this already is the selection
+            if (pos < W) sel[pos] = k;
           }
           running += totc;
-          cons_sync();
+          if (base_k + BM_CONS < ncand) cons_sync();  // wcnt is rewritten by the next chunk
         }
-        if (tid == 0) sc->n_alive = running;
+        n_alive = running;
       }
       cons_sync();
-      const int n_alive = sc->n_alive;
       const int n_sel = n_alive < W ? n_alive : W;
       PF_STAMP(5);
       // ---- phase 4c: the W best alive entries go to sel[rank].
