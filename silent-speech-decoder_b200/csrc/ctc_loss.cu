@@ -34,6 +34,7 @@
 // the frame loop.  Every waiter of a barrier is also part of the chain that lets it complete
 // again (or has a barrier of its own), so a parity can never alias.
 #include <cmath>
+#include <cstring>
 #include <cstdlib>
 
 #include "ssd_common.cuh"
@@ -116,6 +117,9 @@ struct LossParams {
   // second pass after the fp32 fast path (ctc_loss_fast.cu): only utterances with only[b] != 0 are computed
   const int* only;
   const unsigned* only_count;
+  // last resort (rescue_rows below): utterances whose result this kernel could not hold are redone in log space
+  int* rescue;            // [B] non-zero = redo
+  double* rescue_alpha;   // [T][2 S_max + 1] log alpha of the utterance being redone
 };
 
 struct LossSmem {  // byte offsets into dynamic shared memory, identical on host and device
@@ -583,6 +587,11 @@ __device__ void main_role(const LossParams& P, const Half& hf, const Plan& pl, c
           if (dir == 0 && lane == 0) P.nll[pl.b] = (float)(-(log(pm) + (double)eP * 0.69314718055994530942));
         } else if (dir == 0 && lane == 0) {
           P.nll[pl.b] = P.zero_inf ? 0.f : INFINITY;
+          // infeasible, or lost?  A target fits iff its labels plus one blank per repeated label fit the frames;
+          // if it does, the lattice sum was beyond this kernel's reach (thousands of binades inside one strip)
+          int need = pl.S;
+          for (int j = 1; j < pl.S; ++j) need += lab[j] == lab[j - 1] ? 1 : 0;
+          if (need <= pl.Tb) atomicOr(&P.rescue[pl.b], 1);
         }
         if (!want_grad) break;
       }
@@ -707,6 +716,9 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
           }
         }
         __syncwarp();
+        float mass[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) mass[f] = 0.f;
         for (int v = lane; v < V; v += 32) {
           const int ca = cls[v], cb = cls[v + 1];
           float gv[FR], pv[FR];
@@ -718,8 +730,21 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
 #pragma unroll
           for (int f = 0; f < FR; ++f) {
             if (v == P.blank) gv[f] += gb[f];
+            mass[f] += gv[f];
             if (f < nf) st_stream(growp[f] + v, (pv[f] - gv[f]) * scale);
           }
+        }
+        // the posteriors of a frame sum to one; if they do not (or are not numbers) the lattice was beyond what one
+        // exponent per strip can hold, and the utterance is redone in log space after the launch's last utterance
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+          for (int f = 0; f < FR; ++f) mass[f] += __shfl_xor_sync(FULL, mass[f], o);
+        {
+          bool off = false;
+#pragma unroll
+          for (int f = 0; f < FR; ++f) off = off || (f < nf && !(fabsf(mass[f] - 1.f) <= 1e-4f));
+          if (off && lane == 0) atomicOr(&P.rescue[pl.b], 2);
         }
         __syncwarp();
       } else {
@@ -734,6 +759,90 @@ __device__ void grad_role(const LossParams& P, const Half& hf, const Plan& pl, c
     warp_arrive(&hf.bar[B_GEMPTY + ws]);
     warp_arrive(&hf.bar[B_PEMPTY + ps]);
     tstamp(P, 3, pl.h, pl.NP1 + j, 1, uiter);
+  }
+}
+
+// ------------------------------------------------------------------ last resort: one utterance in log space
+// Plain log-space alpha/beta in fp64 (Graves 2006 eqs. 6-8, 10-11, 16 with ATen's conventions), alpha kept in global
+// memory, one CTA, one barrier per frame.  Slow (milliseconds per utterance) and always right: no exponent sharing, no
+// range to leave.  Run by the launch's LAST CTA for the utterances the kernel above flagged: posteriors that did not
+// sum to one, or a feasible target whose lattice sum came out empty -- confident posteriors forced onto an alignment
+// that contradicts them frame after frame put thousands of binades between the cells of ONE strip, which one exponent
+// per strip cannot hold (round-2 fuzz: 164 labels on 175 frames of a posterior laid out for 333; nll 1155).
+__device__ __forceinline__ double lse3(double a, double b, double c) {
+  const double m = fmax(a, fmax(b, c));
+  if (m == -INFINITY) return m;
+  return m + log(exp(a - m) + exp(b - m) + exp(c - m));
+}
+
+__device__ void rescue_row(const LossParams& P, int b, int* lab, double* rowbuf) {
+  const int tid = (int)threadIdx.x;
+  const int64_t tl64 = P.in_len[b], sl64 = P.tg_len[b];
+  const int Tb = (int)tl64, S = (int)sl64, L = 2 * S + 1, V = P.V;
+  const float* x = P.lp + (int64_t)b * P.sb;
+  const float* lse = P.lse ? P.lse + (int64_t)b * P.lse_stride : nullptr;
+  double* alpha = P.rescue_alpha;  // [Tb][L]
+  for (int j = tid; j < S; j += LS_THREADS) lab[j] = (int)P.targets[(int64_t)b * P.tgt_stride + j];
+  __syncthreads();
+  auto lp = [&](int t, int v) { return (double)(x[(int64_t)t * P.st + v] - (lse ? lse[t] : 0.f)); };
+  auto cls_of = [&](int s_) { return (s_ & 1) ? lab[s_ >> 1] : P.blank; };
+  auto skip_ok = [&](int s_) { return (s_ & 1) && s_ >= 3 && lab[s_ >> 1] != lab[(s_ >> 1) - 1]; };
+  // forward
+  for (int s_ = tid; s_ < L; s_ += LS_THREADS) alpha[s_] = s_ < 2 ? lp(0, cls_of(s_)) : -INFINITY;
+  __syncthreads();
+  for (int t = 1; t < Tb; ++t) {
+    const double* ap = alpha + (size_t)(t - 1) * L;
+    double* ac = alpha + (size_t)t * L;
+    for (int s_ = tid; s_ < L; s_ += LS_THREADS)
+      ac[s_] = lse3(ap[s_], s_ >= 1 ? ap[s_ - 1] : -INFINITY, skip_ok(s_) ? ap[s_ - 2] : -INFINITY) + lp(t, cls_of(s_));
+    __syncthreads();
+  }
+  const double* aT = alpha + (size_t)(Tb - 1) * L;
+  const double logZ = lse3(aT[L - 1], L >= 2 ? aT[L - 2] : -INFINITY, -INFINITY);
+  const bool feasible = logZ > -INFINITY;
+  if (tid == 0) P.nll[b] = feasible ? (float)(-logZ) : (P.zero_inf ? 0.f : INFINITY);
+  if (!P.grad) return;
+  float mul = P.grad_mul ? *P.grad_mul : 1.f;
+  if (P.mean_den > 0) mul /= (float)((double)P.mean_den * (double)(S > 1 ? S : 1));
+  float* g = P.grad + (int64_t)b * P.sb;
+  if (!feasible) {
+    const float fill = P.zero_inf ? 0.f : NAN;
+    for (int i = tid; i < Tb * V; i += LS_THREADS) g[(int64_t)(i / V) * P.st + (i % V)] = fill;
+    return;
+  }
+  // backward: beta rows alternate between the two halves of rowbuf; cab = alpha + beta of the current frame
+  double* beta[2] = {rowbuf, rowbuf + L};
+  double* cab = rowbuf + 2 * L;
+  for (int t = Tb - 1; t >= 0; --t) {
+    double* bc = beta[t & 1];
+    const double* bn = beta[(t + 1) & 1];
+    const double* at = alpha + (size_t)t * L;
+    for (int s_ = tid; s_ < L; s_ += LS_THREADS) {
+      double v;
+      if (t == Tb - 1) {
+        v = s_ >= L - 2 ? lp(t, cls_of(s_)) : -INFINITY;
+      } else {
+        const bool skip_fwd = (s_ & 1) && s_ + 2 < L && lab[s_ >> 1] != lab[(s_ >> 1) + 1];
+        v = lse3(bn[s_], s_ + 1 < L ? bn[s_ + 1] : -INFINITY, skip_fwd ? bn[s_ + 2] : -INFINITY) + lp(t, cls_of(s_));
+      }
+      bc[s_] = v;
+      cab[s_] = at[s_] + v;
+    }
+    __syncthreads();
+    for (int v = tid; v < V; v += LS_THREADS) {
+      // log sum over the cells of class v, two passes (maximum, then the sum)
+      double m = -INFINITY;
+      for (int s_ = 0; s_ < L; ++s_)
+        if (cls_of(s_) == v) m = fmax(m, cab[s_]);
+      double acc = 0.0;
+      if (m > -INFINITY)
+        for (int s_ = 0; s_ < L; ++s_)
+          if (cls_of(s_) == v) acc += exp(cab[s_] - m);
+      const double l = lp(t, v);
+      const double post = m > -INFINITY ? exp(m + log(acc) - logZ - l) : 0.0;
+      g[(int64_t)t * P.st + v] = (float)((exp(l) - post) * (double)mul);
+    }
+    __syncthreads();
   }
 }
 
@@ -861,12 +970,29 @@ __global__ void __launch_bounds__(LS_THREADS, MINB) loss_kernel(const LossParams
     jbase += (unsigned)pl.NSEG_RUN;
     __syncthreads();  // label tables are rebuilt for the next utterance
   }
+  // ---------------- the last CTA to get here redoes what was flagged for the log-space path (normally nothing)
+  __shared__ int is_last;
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(P.counter + 2, 1u) == gridDim.x - 1u ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last || !P.rescue_alpha) return;
+  __threadfence();
+  for (int bb = 0; bb < P.B; ++bb) {
+    if (*reinterpret_cast<volatile int*>(P.rescue + bb) == 0) continue;  // uniform: everybody reads the same word
+    // lab (shared) is free now; the beta rows and the per-frame products live at the start of the dynamic shared memory
+    rescue_row(P, bb, lab, reinterpret_cast<double*>(smem));
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------ host side
 struct LossPlan {
   int K, NCmax, VP, Spad, GS, ctas_per_sm, grid, nseg_max;
   size_t smem, ckpt_cta_bytes, ckpt_rec_bytes, ws_bytes;
+  size_t head_bytes, off_ckpt, off_tlog, off_rescue_alpha;  // workspace: [counters | rescue flags][checkpoints][timeline][log alpha]
+  bool rescue_fits;  // the log-space path's three rows fit the shared memory the launch has anyway
 };
 
 static int env_int(const char* name, int dflt) {
@@ -931,7 +1057,12 @@ static bool plan_for(int64_t B, int64_t T, int64_t V, int64_t S_max, LossPlan& p
   pl.nseg_max = (int)((T / 2 + 1 + K - 1) / K + 2);
   pl.ckpt_rec_bytes = (size_t)pl.NCmax * 32 * 8 + 512;  // strip + per-lane e, z, fin
   pl.ckpt_cta_bytes = (size_t)2 * pl.nseg_max * pl.ckpt_rec_bytes;
-  pl.ws_bytes = 256 + (size_t)pl.grid * pl.ckpt_cta_bytes + 8 * 512 * 2 * 8;  // + timeline log
+  pl.head_bytes = 256 + (((size_t)B * 4 + 255) & ~(size_t)255);
+  pl.off_ckpt = pl.head_bytes;
+  pl.off_tlog = pl.off_ckpt + (size_t)pl.grid * pl.ckpt_cta_bytes;
+  pl.off_rescue_alpha = (pl.off_tlog + 8 * 512 * 2 * 8 + 255) & ~(size_t)255;
+  pl.ws_bytes = pl.off_rescue_alpha + (size_t)T * (size_t)(2 * S_max + 1) * 8;
+  pl.rescue_fits = (size_t)3 * (size_t)(2 * S_max + 1) * 8 <= 2 * loss_smem_layout(pl.K, pl.NCmax, (int)V, pl.VP, pl.GS, (int)S_max + 4).half_bytes;
   return true;
 }
 
@@ -964,10 +1095,10 @@ static int loss_launch_t(LossParams& P, const LossPlan& pl, cudaStream_t stream)
 #ifndef SSD_EMU
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
-  e = cudaMemsetAsync(P.counter, 0, 256, stream);
+  e = cudaMemsetAsync(P.counter, 0, pl.head_bytes, stream);  // work queue, exit counter, rescue flags
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "loss: cudaMemsetAsync: %s", cudaGetErrorString(e));
 #else
-  *P.counter = 0u;
+  std::memset(P.counter, 0, pl.head_bytes);
 #endif
   SSD_LAUNCH(kfn, (unsigned)pl.grid, LS_THREADS, pl.smem, stream, P);
   return check_launch("loss_kernel");
@@ -1007,13 +1138,15 @@ int loss_launch(const float* lp, const float* lse, int64_t lse_stride, int64_t B
   P.blank = blank; P.zero_inf = zero_inf; P.mean_den = mean_den; P.grad_mul = grad_mul;
   P.nll = nll; P.grad = grad;
   P.counter = reinterpret_cast<unsigned*>(ws);
-  P.ckpt = reinterpret_cast<unsigned char*>(ws) + 256;
+  P.rescue = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + 256);
+  P.rescue_alpha = pl.rescue_fits && !env_int("SSD_LOSS_NORESCUE", 0) ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + pl.off_rescue_alpha) : nullptr;
+  P.ckpt = reinterpret_cast<unsigned char*>(ws) + pl.off_ckpt;
   P.ckpt_cta_bytes = pl.ckpt_cta_bytes; P.ckpt_rec_bytes = pl.ckpt_rec_bytes; P.nseg_max = pl.nseg_max;
   P.K = pl.K; P.NCmax = pl.NCmax; P.VP = pl.VP; P.Spad = pl.Spad; P.GS = pl.GS;
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
   if (env_int("SSD_LOSS_NOTMA", 0)) P.use_tma = 0;  // tuning knob
   P.dbg = env_int("SSD_LOSS_DBG", 0);
-  P.tlog = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ws) + pl.ws_bytes - 8 * 512 * 2 * 8);
+  P.tlog = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ws) + pl.off_tlog);
   switch (pl.NCmax) {
     case 4: return loss_launch_t<4, 2>(P, pl, stream);
     case 8: return loss_launch_t<8, 2>(P, pl, stream);

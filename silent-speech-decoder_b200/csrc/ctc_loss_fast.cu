@@ -131,10 +131,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 #endif
 }
-// exp(lp) = ex2(lp * log2 e): two instructions.  The rounding of the product costs |lp * log2 e| * 2^-24 relative
-// (3e-7 at lp = -4, 2e-6 at lp = -20), i.e. it acts like a perturbation of the input far below the 1e-5 the
-// result is held to; inputs beyond +-F_LP_ABS are flagged by the caller (D1) and never reach a result.
-__device__ __forceinline__ float prob_f(float lp) { return ex2_approx(lp * 1.4426950408889634f); }
+// exp(lp) = ex2(lp * log2 e), with the product's rounding error put back: t = lp * L2E carries |t| * 2^-24 of error in
+// the EXPONENT, i.e. a relative error of |t| * 4e-8 in p (1e-6 at lp = -17, the level of an unlikely label under
+// confident posteriors).  Over hundreds of frames of a tiny lattice that perturbation showed up as 1.4e-5 in the
+// gradient (round-2 fuzz: one label on 600 confident frames), above the 1e-5 the result is held to.  The residual of
+// the product (one FMA) plus the low half of log2 e goes in as a first-order correction: what is left is ex2.approx's
+// own 2^-22.  Inputs beyond +-F_LP_ABS are flagged by the caller (D1) and never reach a result.
+__device__ __forceinline__ float prob_f(float lp) {
+  const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-08f;
+  const float t = lp * L2E_HI;
+  const float d = fmaf(lp, L2E_LO, fmaf(lp, L2E_HI, -t));  // what t misses of lp * log2 e
+  const float q = ex2_approx(t);
+  return fmaf(q * 0.6931471805599453f, d, q);  // 2^(t+d) = q * (1 + d ln 2) to first order (|d| < 2^-20)
+}
 __device__ __forceinline__ float ld_cg(const float* p) {
 #ifdef SSD_EMU
   return *p;
@@ -186,7 +195,7 @@ struct FastParams {
   int region_by_sm;      // 1: more utterances than checkpoint regions, a CTA takes one of its SM's two regions and returns it
   int pdl_wait;          // first class kernel after the prepass: wait for it (programmatic dependent launch)
   int direct;            // 1: no prepass -- one kernel takes all B utterances in the caller's order (B <= checkpoint regions)
-  int* flags;          // [B] non-zero = recompute on the exact path (1 not covered, 2 D1, 4 D2, 8 D3, 16 D4)
+  int* flags;          // [B] non-zero = recompute on the exact path (1 not covered, 2 D1, 4 D2, 8 D3, 16 D4, 32 D5)
   unsigned char* ckpt; // per CTA: [2 dirs][nb_max] records
   size_t ckpt_cta_bytes, ckpt_rec_bytes;
   int nb_max;
@@ -978,6 +987,10 @@ __device__ void fast_worker(const FastParams& P, const FPlan& pl, const int* __r
             inv_zm = 1.f / zm;
             ez = Qm + et;
             if (lane == 0) P.nll[pl.b] = (float)(-(log((double)zm) + (double)ez * 0.69314718055994530942));
+            // D5: Z above 1/8, i.e. nll below ~2 (a handful of frames with confident posteriors).  Z carries fp32's
+            // ~4e-7 relative error; -log amplifies it by 1/nll, and 1e-5 of the nll is what the result is held to.
+            // Such an utterance is tiny: the exact path takes it.  (A training-length utterance has nll >> 2.)
+            if (ez >= -3 && lane == 0) atomicOr(&sc->uflag, 32);
           } else if (lane == 0) {
             atomicOr(&sc->uflag, 16);  // D4: infeasible or lost -- the exact path decides which
           }

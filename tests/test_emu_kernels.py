@@ -289,3 +289,23 @@ def test_scale_if(lib):
     x = np.random.default_rng(0).standard_normal(1003).astype(np.float32)
     assert np.array_equal(harness.scale_if(lib, x, 0.65, 0.65), x)  # matches what was expected: untouched
     np.testing.assert_allclose(harness.scale_if(lib, x, 1.3, 0.65), x * np.float32(2.0), rtol=1e-6)
+
+
+def test_loss_extreme_mismatch_is_redone_in_log_space(lib):
+    """Found by the round-2 fuzz: confident posteriors laid out for 333 frames, input cut to ~170 frames, 137-164 labels
+    (every frame contradicts the forced alignment: nll ~ 900-1150, thousands of binades inside one strip).  The fp32
+    kernel flags such a row, the fp64 kernel cannot hold it either (one exponent per strip) and flags it for the
+    log-space pass run by the launch's last CTA; what comes back is the reference's value, not NaN."""
+    B, T, S, c = 600, 333, 255, 52
+    lp, tg, tl = synth.peaked_aligned(B, T, 7000 + c, n_labels=(1, T // 2))
+    tg = torch.nn.functional.pad(tg, (0, S - tg.size(1)))
+    il = synth.ragged_lengths(B, T, 9000 + c)
+    rows = [8, 31, 5]  # il 169 / tl 137, il 175 / tl 164, and an ordinary neighbour
+    sel = torch.tensor(rows)
+    assert il[sel].tolist() == [169, 175, 199] and tl[sel].tolist() == [137, 164, 38]
+    nll, grad = harness.loss(lib, lp[sel].numpy(), il[sel].numpy(), tg[sel].numpy(), tl[sel].numpy(), 1, True, mean_den=3)
+    n64, _, g64 = ol.torch_ctc(lp[sel], il[sel], tg[sel], tl[sel], 1, True, torch.float64)
+    assert np.isfinite(grad).all()
+    np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+    err = np.abs(grad - g64.numpy()).reshape(3, -1).max(1)
+    assert (err <= 1e-5 * np.abs(g64.numpy()).reshape(3, -1).max(1)).all(), err

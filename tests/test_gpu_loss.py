@@ -394,3 +394,24 @@ def test_device_resident_bad_lengths(monkeypatch):
     monkeypatch.setenv("SSD_VALIDATE_LENGTHS", "1")
     with pytest.raises(RuntimeError):
         CTCLoss(blank=1)(lp, tg.cuda(), il, tl.cuda())
+
+
+@pytest.mark.timeout(120)
+def test_extreme_mismatch_is_redone_in_log_space():
+    """The fuzz-found rows of tests/test_emu_kernels.py::test_loss_extreme_mismatch_is_redone_in_log_space inside a batch
+    of ordinary ones, on the GPU: both self-checking kernels hand them down, the log-space pass returns the reference's
+    values; the ordinary rows are untouched by it."""
+    B, T, S, c = 600, 333, 255, 52
+    lp, tg, tl = synth.peaked_aligned(B, T, 7000 + c, n_labels=(1, T // 2))
+    tg = torch.nn.functional.pad(tg, (0, S - tg.size(1)))
+    il = synth.ragged_lengths(B, T, 9000 + c)
+    sel = torch.arange(0, 64)
+    lp, tg, tl, il = lp[sel], tg[sel], tl[sel], il[sel]
+    nll, grad = ops.ctc_loss_fwd_bwd(lp.cuda(), il, tg, tl, blank=1, mean_denominator=64)
+    n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+    assert torch.isfinite(grad).all()
+    fin = torch.isfinite(n64) & (n64 != 0)
+    assert ((nll.cpu().double() - n64)[fin].abs() / n64[fin].abs()).max().item() < RTOL
+    err = (grad.cpu().double() - g64).abs().amax(dim=(1, 2))
+    ref = g64.abs().amax(dim=(1, 2))
+    assert (err <= RTOL * ref + 1e-12).all(), (err / ref.clamp_min(1e-30)).max().item()
