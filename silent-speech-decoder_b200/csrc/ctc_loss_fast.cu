@@ -112,7 +112,13 @@ constexpr int F_RANK_MAX = 1024;  // batches up to this size are ranked by cost 
 #define SSD_F_REBASE 32
 #endif
 constexpr int F_REBASE = SSD_F_REBASE;  // a live neighbour this many binades above me: take its exponent (my cells shrink, its inflow stays finite)
-constexpr float F_MASS_TOL = 1.5e-5f;
+// D3's tolerance on a frame's posterior mass.  What the result is held to is 1e-5 of max |gradient|, and a mass error of
+// m shows up as about m in the posteriors: 1.5e-5 (round 1) let a row through that was 2.5e-5 off (round-2 fuzz: one
+// label on 176 confident frames).  Ordinary rows sit at 1-3e-6: 6e-6 flags nothing at config 2, flat or trained.
+#ifndef SSD_F_MASS_TOL
+#define SSD_F_MASS_TOL 6e-6f
+#endif
+constexpr float F_MASS_TOL = SSD_F_MASS_TOL;
 constexpr float F_LP_ABS = 80.f;  // log-probs beyond +-80 (or NaN) send the utterance to the exact path
 
 // ------------------------------------------------------------------ scalar helpers
