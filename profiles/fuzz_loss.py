@@ -62,6 +62,20 @@ for c in range(cases):
         os._exit(3)
     fin = torch.isfinite(nll_x)
     assert torch.equal(torch.isfinite(nll), fin), tag
+    # the exact kernel itself against the reference's ATen op in fp64 on the host (bounded sizes: seconds of CPU)
+    et = 0.0
+    if B * T <= 120000:
+        from oracle import ctc_loss as ol
+
+        n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+        f64 = torch.isfinite(n64) & (n64 != 0)
+        assert torch.isfinite(g_x).all(), tag + " (non-finite gradient from the exact path)"
+        if f64.any():
+            et = float(((nll_x.cpu().double() - n64)[f64].abs() / n64[f64].abs().clamp_min(1e-3)).max())
+        et = max(et, float((g_x.cpu().double() - g64).abs().max() / g64.abs().max().clamp_min(1e-30)))
+        if et > 1e-5:
+            print("BAD " + tag, f"exact path vs torch fp64: {et:.1e}", flush=True)
+            os._exit(2)
     en = float(((nll[fin] - nll_x[fin]).abs() / nll_x[fin].abs().clamp_min(1e-3)).max()) if fin.any() else 0.0
     eg = float((g - g_x).abs().max() / g_x.abs().max().clamp_min(1e-30))
     worst_n, worst_g = max(worst_n, en), max(worst_g, eg)
