@@ -415,3 +415,20 @@ def test_extreme_mismatch_is_redone_in_log_space():
     err = (grad.cpu().double() - g64).abs().amax(dim=(1, 2))
     ref = g64.abs().amax(dim=(1, 2))
     assert (err <= RTOL * ref + 1e-12).all(), (err / ref.clamp_min(1e-30)).max().item()
+
+
+def test_device_prefetcher_delivers_every_batch_intact():
+    """data/prefetch.py: two alternating device buffer sets, copies one batch ahead on a side stream.  Every batch must
+    arrive with its own contents while the consumer is still busy with the previous one."""
+    from silent_speech_decoder_b200.data.prefetch import DevicePrefetcher
+
+    host = [(torch.full((64, 300, 48), float(i)).pin_memory(), torch.tensor([i, i + 1]).pin_memory()) for i in range(7)]
+    sums = []
+    for x, n in DevicePrefetcher(iter(host), torch.device("cuda", 0)):
+        y = x
+        for _ in range(20):  # keep the consumer's stream busy so that the next copy really overlaps
+            y = y * 1.0000001
+        sums.append((float(x[0, 0, 0]), float(y.mean()), n.tolist()))
+    assert [s[0] for s in sums] == [float(i) for i in range(7)]
+    assert [s[2] for s in sums] == [[i, i + 1] for i in range(7)]
+    assert all(abs(s[1] - s[0]) <= 1e-4 * max(1.0, s[0]) for s in sums)
