@@ -583,10 +583,14 @@ def bench_cfg5(args, rank, world, dev):
         warm = [None] * world if rank == 0 else None
         dist.gather_object([{"utterance_id": -1, "ref": "", "hyp": ""}], warm, dst=0)
     barrier(world)
+    from silent_speech_decoder_b200 import ops
+
+    l0 = sum(ops.LAUNCHES.values())
     t0 = time.perf_counter()
     e, enc_ms = run()
     torch.cuda.synchronize()
     local_s = time.perf_counter() - t0
+    native_launches = sum(ops.LAUNCHES.values()) - l0
     # transcripts to rank 0 (a few hundred KB of text)
     if world > 1:
         gathered = [None] * world if rank == 0 else None
@@ -601,7 +605,7 @@ def bench_cfg5(args, rank, world, dev):
            "value": c["N"] / total_s, "unit": "utterances/s", "seconds": total_s, "scaling": "strong",
            "encoder_share": dist_max(enc_ms * 1e-3, world, dev) / total_s,
            "decode_and_host_share": 1.0 - dist_max(enc_ms * 1e-3, world, dev) / total_s,
-           "rank0_local_seconds": local_s}
+           "rank0_local_seconds": local_s, "native_launches": native_launches}
     if rank == 0:
         from silent_speech_decoder_b200.evaluation import evaluate as evm
 
@@ -628,7 +632,7 @@ def run_native(args, rank, world, local):
             r = bench_cfg5(args, rank, world, dev)
             line = {"metric": "evaluate_pipeline_utterances_per_sec", "value": r["value"], "unit": "utterances/s", "ms_per_step": 1e3 * r["seconds"],
                     "dtype": "f32", "config": r["config"], "e2e": {"value": r["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                    "gpu_launches": 0, "roofline": None, "cfg5": r}
+                    "gpu_launches": r["native_launches"], "roofline": None, "cfg5": r}
         else:
             line = bench_decode(args, rank, world, dev, args.workload, args.beam_input, args.utts, args.T, args.width, CFG3["seed"] if args.T == CFG3["T"] else CFG4["seed"])
         if args.workload == "loss" and not args.no_secondary:
