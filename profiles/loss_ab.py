@@ -9,7 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import bench
-from silent_speech_decoder_b200 import synth
+from silent_speech_decoder_b200 import _native, synth
+
+if os.environ.get("SSD_LIB"):  # a variant build (profiles/build_variant.sh)
+    from pathlib import Path
+    _native._LIB = _native.Library(Path(os.environ["SSD_LIB"]).resolve())
 
 dev = torch.device("cuda", 0)
 out = {"tag": sys.argv[1] if len(sys.argv) > 1 else "", "env": {k: v for k, v in os.environ.items() if k.startswith("SSD_")}}

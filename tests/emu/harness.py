@@ -17,7 +17,9 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 REPO = HERE.parent.parent
 CSRC = REPO / "silent-speech-decoder_b200" / "csrc"
-OUT = HERE / "_build"
+# SSD_EMU_FLAGS: extra -D flags for a variant build (kept in its own directory), e.g. "-DSSD_F_DENSE=0"
+EXTRA = os.environ.get("SSD_EMU_FLAGS", "").split()
+OUT = HERE / ("_build" + ("_" + "".join(c if c.isalnum() else "_" for c in " ".join(EXTRA)) if EXTRA else ""))
 LIB = OUT / "libssd_ctc_emu.so"
 SOURCES = ["greedy.cu", "beam.cu", "ctc_loss.cu", "ctc_loss_fast.cu", "edit.cu", "aux.cu", "capi.cu"]
 
@@ -30,7 +32,7 @@ def build(force: bool = False) -> Path:
 
     def cc(src):
         obj = OUT / (Path(src).stem + ".o")
-        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-DSSD_EMU", "-I", str(HERE), "-I", str(CSRC), "-x", "c++", "-c",
+        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-DSSD_EMU", *EXTRA, "-I", str(HERE), "-I", str(CSRC), "-x", "c++", "-c",
                str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
