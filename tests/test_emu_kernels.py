@@ -309,3 +309,27 @@ def test_loss_extreme_mismatch_is_redone_in_log_space(lib):
     np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
     err = np.abs(grad - g64.numpy()).reshape(3, -1).max(1)
     assert (err <= 1e-5 * np.abs(g64.numpy()).reshape(3, -1).max(1)).all(), err
+
+
+def test_loss_fast_path_long_classes(lib):
+    """Skewed label histograms: the most frequent classes are summed by the whole warp (fast_worker, "long" classes),
+    the rest by the per-lane range loop.  One dominant label, a few frequent ones, and a vocabulary of 70 (three
+    class passes in two trips, long classes in different passes) -- all must stay on the fp32 path and meet the tolerance."""
+    g = torch.Generator().manual_seed(11)
+    for B, T, S, Vn, hot in ((3, 300, 120, 48, [(5, 0.6)]), (3, 260, 100, 48, [(7, 0.3), (40, 0.2), (33, 0.15)]),
+                             (2, 300, 110, 70, [(3, 0.25), (40, 0.25), (69, 0.2), (36, 0.1)])):
+        w = torch.ones(Vn)
+        w[0] = w[1] = 0.0
+        rest = 1.0 - sum(p for _, p in hot)
+        w = w / w.sum() * rest
+        for v, p in hot:
+            w[v] += p
+        tg = torch.multinomial(w, B * S, replacement=True, generator=g).reshape(B, S)
+        tl = torch.full((B,), S)
+        il = torch.full((B,), T)
+        lp = synth.flat(B, T, 100 + S, Vn)
+        nll, grad, flags = harness.loss(lib, lp.numpy(), il.numpy(), tg.numpy(), tl.numpy(), 1, True, mean_den=B, with_fallbacks="flags")
+        assert flags.tolist() == [0] * B
+        n64, _, g64 = ol.torch_ctc(lp, il, tg, tl, 1, True, torch.float64)
+        np.testing.assert_allclose(nll, n64.numpy(), rtol=1e-5)
+        assert np.abs(grad - g64.numpy()).max() <= 1e-5 * g64.abs().max().item()
