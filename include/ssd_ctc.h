@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SSD_ABI_VERSION 2
+#define SSD_ABI_VERSION 3
 
 enum {
   SSD_OK = 0,
@@ -53,6 +53,7 @@ enum {
 #define SSD_MAX_BEAM 512       /* beam_width */
 #define SSD_MAX_BEAM_SETTINGS 8 /* decoder settings served by one ssd_ctc_beam_grid launch */
 #define SSD_MAX_EDIT_LEN 8191  /* tokens per sequence in ssd_edit_counts */
+#define SSD_MAX_LM_ORDER 6     /* n-gram order of the language model of ssd_ctc_beam_lm */
 
 int ssd_abi_version(void);
 const char* ssd_last_error(void);
@@ -111,6 +112,52 @@ int ssd_ctc_beam_grid(const float* log_probs, int64_t B, int64_t T, int64_t V, i
                       const int64_t* lengths, const int32_t* order, int blank, int pad, int space,
                       const ssd_beam_setting* settings, int n_settings, int32_t* out_tokens, int32_t* out_lengths,
                       double* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Prefix beam search fused with a word n-gram language model (scope row f-4): what
+ * src/decoding/ctc.py:67-72 sets up when lm_path is given -- pyctcdecode.build_ctcdecoder(labels,
+ * kenlm_model_path=<ARPA file of src/decoding/build_char_lm.py:35-40>, alpha, beta) -- and :91-95 runs.
+ * A beam is ranked and pruned by  acoustic score + LM score of its closed words + partial-word score:
+ *   closed word w after state h   alpha * ln10 * (log10 p(w | h) [+ unk_score_offset if w is out of vocabulary])
+ *                                 + beta, back-off scoring as kenlm's BaseScore, start state <s>
+ *   open word                     unk_score_offset if it is not a prefix of any unigram, times len/6 beyond 6 chars
+ *   end of utterance              the last word also gets log10 p(</s> | ...), unless its text was already
+ *                                 scored as a closed text earlier in the utterance (upstream's score cache)
+ *   history prune                 key = (last order-1 closed words, open word, last char)
+ * The tables are DEVICE arrays built by the caller from the ARPA file (host side: decoding/lm.py):
+ *   trie_child  [n_trie_nodes, n_labels] int32: node reached from `node` by beam label k (label 0 = blank is
+ *               unused; labels are numbered as in ssd_ctc_beam: blank, then the vocabulary ids without blank
+ *               and pad, ascending), or -1.  Node 0 is the root.  The trie holds the unigrams' spellings.
+ *   trie_word   [n_trie_nodes] int32: word id spelled by the path to this node, or -1
+ *   ngram_*     forward trie of n-grams as an open-addressing hash table with linear probing: an n-gram
+ *               (w1..wn) has an id; unigram ids ARE the word ids; the table maps
+ *               key = ((id(w1..w_{n-1}) + 1) << 32) | wn  to id(w1..wn), slot = ssd_lm_hash(key) & ngram_mask,
+ *               empty slots hold key 0.  ngram_prob / ngram_backoff [n_ngrams] fp32 log10 values by id.
+ *   bos / eos / unk   word ids of <s>, </s>, <unk> (-1 when the file has none)
+ * out_scores receives the RANKING score (acoustic + LM) of the best transcript.
+ * Limits: order <= SSD_MAX_LM_ORDER; every beam proposes every candidate label (the no-LM kernel's staircase
+ * bound does not hold under LM scores), so shared memory limits beam_width to ~100 at 47 labels.
+ */
+typedef struct ssd_lm_tables {
+  const int32_t* trie_child;
+  const int32_t* trie_word;
+  const uint64_t* ngram_keys;
+  const int32_t* ngram_vals;
+  const float* ngram_prob;
+  const float* ngram_backoff;
+  uint64_t ngram_mask; /* slots - 1, slots a power of two */
+  int32_t n_trie_nodes, n_labels, n_ngrams, order;
+  int32_t bos, eos, unk, reserved;
+  double alpha, beta, unk_score_offset;
+} ssd_lm_tables;
+/* slot hash of the n-gram table: h = key * 0x9E3779B97F4A7C15 (mod 2^64), h ^ (h >> 29).  Exported so that a host
+ * builder in any language can check its own copy against the library's. */
+uint64_t ssd_lm_hash(uint64_t key);
+size_t ssd_ctc_beam_lm_workspace_bytes(int64_t B, int64_t T, int64_t V, int beam_width);
+int ssd_ctc_beam_lm(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                    const int64_t* lengths, const int32_t* order, int blank, int pad, int space,
+                    const ssd_beam_setting* settings, int n_settings, const ssd_lm_tables* lm, int32_t* out_tokens,
+                    int32_t* out_lengths, double* out_scores, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * CTC loss, forward and backward in one launch (torch.nn.CTCLoss semantics, reduction 'none'

@@ -138,19 +138,42 @@ def _merge(beams):
 
 def _score_no_lm(beams):
     # without LM / hotwords the ranking score is the acoustic score; text absorbs next_word
-    return [(_join(text, nxt), "", part, last, score) for text, nxt, part, last, score in beams]
+    return [(_join(text, nxt), "", part, last, score, score) for text, nxt, part, last, score in beams]
+
+
+def _score_lm(beams, lm, cache, pcache, is_eos: bool = False):
+    """``_get_lm_beams``: ranking score = acoustic score + LM score of the closed text + partial-word score.
+    ``cache`` maps a closed text to (accumulated LM score, end state) and is shared by every frame of an
+    utterance AND by the final end-of-sentence pass -- so, as upstream, a text that was scored before keeps
+    its score without the </s> term."""
+    out = []
+    for text, nxt, part, last, score in beams:
+        new_text = _join(text, nxt)
+        if new_text not in cache:
+            prev, state = cache[text]
+            s, end_state = lm.score(state, nxt, is_last_word=is_eos)
+            cache[new_text] = (prev + s, end_state)
+        lm_score = cache[new_text][0]
+        if part:
+            if part not in pcache:
+                pcache[part] = lm.score_partial_token(part)
+            lm_score += pcache[part]
+        out.append((new_text, "", part, last, score, score + lm_score))
+    return out
 
 
 def _cut(beams, beam_width: int, beam_prune_logp: float):
-    top = max(b[4] for b in beams)
-    alive = [b for b in beams if b[4] >= top + beam_prune_logp]
-    return heapq.nlargest(beam_width, alive, key=lambda b: b[4])
+    # ranked and pruned by the LAST field (acoustic + LM); the acoustic score [4] is what the beam carries on
+    top = max(b[-1] for b in beams)
+    alive = [b for b in beams if b[-1] >= top + beam_prune_logp]
+    return heapq.nlargest(beam_width, alive, key=lambda b: b[-1])
 
 
 def _history_prune(beams, keep_words: int = 1):
     seen = set()
     out = []
-    for text, nxt, part, last, score in beams:
+    for b in beams:
+        text, nxt, part, last, score = b[:5]
         key = (tuple(text.split()[-keep_words:]), part, last)
         if key not in seen:
             seen.add(key)
@@ -165,9 +188,19 @@ def search(
     beam_prune_logp: float,
     token_min_logp: float = DEFAULT_TOKEN_MIN_LOGP,
     prune_history: bool = True,
-) -> List[Tuple[str, float]]:
-    """``_decode_logits`` with no LM.  rows: conditioned (T,len(labels)) log-probs.
-    Returns the final beams as (text, score), best first."""
+    lm=None,
+    with_lm_score: bool = False,
+) -> List[Tuple]:
+    """``_decode_logits``.  rows: conditioned (T,len(labels)) log-probs; ``lm``: an ``oracle.lm.LanguageModel``
+    or None.  Returns the final beams as (text, acoustic score), best first -- with ``with_lm_score`` as
+    (text, acoustic score, ranking score)."""
+    cache = {"": (0.0, lm.start_state())} if lm is not None else None
+    pcache: dict = {}
+    keep_words = max(1, lm.order - 1) if lm is not None else 1
+
+    def rank(merged, is_eos=False):
+        return _score_no_lm(merged) if lm is None else _score_lm(merged, lm, cache, pcache, is_eos)
+
     beams = [("", "", "", None, 0.0)]
     for row in rows:
         cand = set(np.where(row >= token_min_logp)[0].tolist()) | {int(row.argmax())}
@@ -182,11 +215,13 @@ def search(
                     grown.append((text, part, "", ch, score + p))
                 else:
                     grown.append((text, nxt, part + ch, ch, score + p))
-        kept = _cut(_score_no_lm(_merge(grown)), beam_width, beam_prune_logp)
-        beams = _history_prune(kept) if prune_history else kept
+        kept = _cut(rank(_merge(grown)), beam_width, beam_prune_logp)
+        beams = _history_prune(kept, keep_words) if prune_history else [b[:5] for b in kept]
     closed = [(text, part, "", None, score) for text, _, part, _, score in beams]
-    final = _cut(_score_no_lm(_merge(closed)), beam_width, beam_prune_logp)
-    return [(" ".join(text.split()), score) for text, _, _, _, score in final]
+    final = _cut(rank(_merge(closed), is_eos=True), beam_width, beam_prune_logp)
+    if with_lm_score:
+        return [(" ".join(b[0].split()), b[4], b[5]) for b in final]
+    return [(" ".join(b[0].split()), b[4]) for b in final]
 
 
 # --------------------------------------------------------------------------- reference-shaped API
@@ -203,7 +238,9 @@ class BeamDecoder:
         beam_prune_logp: float = -10.0,
         blank_bias: float = 0.0,
         token_min_logp: float = DEFAULT_TOKEN_MIN_LOGP,
+        lm=None,
     ):
+        self.lm = lm  # oracle.lm.LanguageModel, what build_ctcdecoder(kenlm_model_path=..., alpha, beta) sets up
         self.blank_id, self.pad_id = blank_id, pad_id
         self.beam_width, self.beam_prune_logp = beam_width, beam_prune_logp
         self.blank_bias, self.token_min_logp = blank_bias, token_min_logp
@@ -217,8 +254,14 @@ class BeamDecoder:
         out = []
         for i, n in enumerate(lengths):
             rows = condition_rows(mat[i, : int(n)])
-            out.append(search(rows, self.labels, self.beam_width, self.beam_prune_logp, self.token_min_logp)[0])
+            out.append(search(rows, self.labels, self.beam_width, self.beam_prune_logp, self.token_min_logp, lm=self.lm)[0])
         return out
+
+    def decode_with_lm_scores(self, log_probs, lengths) -> List[Tuple[str, float, float]]:
+        """(text, acoustic score, acoustic + LM score) of the best beam per utterance."""
+        mat = wrapper_matrix(np.asarray(log_probs), self.blank_id, self.pad_id, self.blank_bias, self.keep)
+        return [search(condition_rows(mat[i, : int(n)]), self.labels, self.beam_width, self.beam_prune_logp,
+                       self.token_min_logp, lm=self.lm, with_lm_score=True)[0] for i, n in enumerate(lengths)]
 
     def __call__(self, log_probs, lengths) -> List[str]:
         return [t for t, _ in self.decode_with_scores(log_probs, lengths)]

@@ -10,7 +10,7 @@ import ctypes as C
 from pathlib import Path
 from typing import Optional
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LIB_PATH = Path(__file__).resolve().parent / "libssd_ctc.so"
 
 SSD_OK, SSD_ERR_BAD_ARG, SSD_ERR_UNSUPPORTED, SSD_ERR_WORKSPACE, SSD_ERR_CUDA = range(5)
@@ -24,6 +24,9 @@ SIGNATURES = {
     "ssd_ctc_beam_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "ssd_ctc_beam": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _F32, _I32, _F32, _F32, _P, _P, _P, _P, _SZ, _P]),
     "ssd_ctc_beam_grid": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "ssd_lm_hash": (C.c_uint64, [C.c_uint64]),
+    "ssd_ctc_beam_lm_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
+    "ssd_ctc_beam_lm": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "ssd_ctc_loss_from_logits_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "ssd_ctc_loss_from_logits": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "ssd_row_logsumexp": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
@@ -40,6 +43,18 @@ class BeamSetting(C.Structure):
     """``ssd_beam_setting`` of include/ssd_ctc.h."""
 
     _fields_ = [("beam_width", C.c_int32), ("beam_prune_logp", C.c_float), ("blank_bias", C.c_float), ("token_min_logp", C.c_float)]
+
+
+class LmTables(C.Structure):
+    """``ssd_lm_tables`` of include/ssd_ctc.h (device pointers + scalars)."""
+
+    _fields_ = [
+        ("trie_child", C.c_void_p), ("trie_word", C.c_void_p), ("ngram_keys", C.c_void_p), ("ngram_vals", C.c_void_p),
+        ("ngram_prob", C.c_void_p), ("ngram_backoff", C.c_void_p), ("ngram_mask", C.c_uint64),
+        ("n_trie_nodes", C.c_int32), ("n_labels", C.c_int32), ("n_ngrams", C.c_int32), ("order", C.c_int32),
+        ("bos", C.c_int32), ("eos", C.c_int32), ("unk", C.c_int32), ("reserved", C.c_int32),
+        ("alpha", C.c_double), ("beta", C.c_double), ("unk_score_offset", C.c_double),
+    ]
 
 
 class NativeError(RuntimeError):

@@ -86,7 +86,15 @@ struct BeamParams {
   int VL;     // labels after dropping blank/pad: 1 + #others
   int TS;     // hash table slots (pow2)
   int NCAND;  // candidate capacity
+  // language-model fusion (beam_kernel<true> only; scope row f-4)
+  ssd_lm_tables lm;
+  double lm_factor;           // 1 / log10(e): log10 -> ln, as upstream's LOG_BASE_CHANGE_FACTOR
+  unsigned long long* seen;   // [grid][seen_cap] closed texts that were LM-scored (upstream's cached_lm_scores keys)
+  int64_t seen_cap;           // slots per CTA (pow2)
 };
+
+// candidate capacity under LM scores: every live prefix proposes every non-blank label (no staircase bound)
+__host__ __device__ inline int beam_ncand_cap_lm(int W, int VL) { return (2 * W + W * (VL - 1) + 31) / 32 * 32; }
 
 __host__ __device__ inline int beam_ncand_cap(int W, int VL) {
   // 2 entries per live prefix + staircase sum_{i<W} min(VL-1, W/(i+1)+1)
@@ -225,9 +233,19 @@ __host__ __device__ inline size_t beam_scratch_bytes(int W, int NCAND) {
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
-__host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND) {
+// per-prefix language-model state, one generation: accumulated LM score of the closed words (fp64), n-gram context
+// ids (order-1, at least one slot), trie node and length of the open word, hashes of the 2nd.. last closed words
+__host__ __device__ inline int lm_ctx_slots(int order) { return order > 1 ? order - 1 : 1; }
+__host__ __device__ inline size_t lm_gen_bytes(int W, int order) {
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const int cx = lm_ctx_slots(order);
+  return al(8 * (size_t)W) + 2 * al(4 * (size_t)W) + al(4 * (size_t)W * cx) + al(8 * (size_t)W * cx);
+}
+
+__host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND, int lm_order = 0) {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t s = 0;
+  if (lm_order > 0) s += 2 * lm_gen_bytes(W, lm_order) + al(8 * (size_t)NCAND);  // LM state x2, ranking scores
   s += 2 * prefix_gen_bytes(W);                              // prefix tables, two generations
   s += 3 * al(8 * (size_t)W);                               // tot, newb, newnb
   s += 5 * al(4 * (size_t)W);                               // par, rank2p, rowoff, keepflags, slot
@@ -401,8 +419,94 @@ __device__ __noinline__ void load_rows_strided(float* __restrict__ dst, const fl
   __syncwarp();
 }
 
+// ------------------------------------------------------------------ language model (beam_kernel<true>)
+// Restates what pyctcdecode's LanguageModel does with a kenlm.Model (oracle/lm.py has the same arithmetic in numpy):
+// back-off scoring over a forward trie of n-grams held as a hash table in global memory, unigram spellings as a
+// dense character trie.  All tables are read-only and L2-resident for LMs of the reference's size.
+constexpr int LM_CX = SSD_MAX_LM_ORDER - 1;  // context words / history words kept per prefix, at most
+
+__device__ __forceinline__ uint64_t lm_hash(uint64_t key) {
+  const uint64_t h = key * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+// id of the n-gram (context n-gram `parent`, word w), or -1
+__device__ inline int lm_child(const ssd_lm_tables& L, int parent, int w) {
+  const uint64_t key = ((uint64_t)(uint32_t)(parent + 1) << 32) | (uint64_t)(uint32_t)w;
+  uint64_t s = lm_hash(key) & L.ngram_mask;
+  for (;;) {
+    const uint64_t k = L.ngram_keys[s];
+    if (k == key) return L.ngram_vals[s];
+    if (k == 0ull) return -1;
+    s = (s + 1) & L.ngram_mask;
+  }
+}
+// kenlm BaseScore: log10 p(w | ctx) in fp32.  ctx[j] = id of the n-gram made of the last j+1 context words (-1: not
+// in the model).  The longest n-gram ending in w gives the probability; every context longer than the matched one
+// adds its back-off weight, shorter contexts first.  new_ctx (may be null) receives the state after w.
+__device__ inline float lm_base_score(const ssd_lm_tables& L, const int* ctx, int w, int* new_ctx) {
+  const int C = L.order - 1;
+  const int wid = w >= 0 ? w : L.unk;  // out of vocabulary -> <unk>
+  float prob = wid >= 0 ? L.ngram_prob[wid] : -100.f;
+  int matched = 1;
+  if (new_ctx) {
+    for (int j = 0; j < C; ++j) new_ctx[j] = -1;
+    if (C > 0) new_ctx[0] = wid;
+  }
+  if (wid >= 0) {
+    for (int j = 0; j < C; ++j) {
+      if (ctx[j] < 0) break;
+      const int id = lm_child(L, ctx[j], wid);
+      if (id < 0) break;
+      prob = L.ngram_prob[id];
+      matched = j + 2;
+      if (new_ctx && j + 1 < C) new_ctx[j + 1] = id;
+    }
+  }
+  for (int j = matched - 1; j < C; ++j)
+    if (ctx[j] >= 0) prob = prob + L.ngram_backoff[ctx[j]];
+  return prob;
+}
+// LanguageModel.score: alpha * (BaseScore [+ unk offset] [+ BaseScore(</s>)]) * ln10 + beta, in fp64 over fp32 terms
+__device__ inline double lm_word_score(const ssd_lm_tables& L, double factor, const int* ctx, int w, bool eos, int* new_ctx) {
+  int st[LM_CX];
+  double lm = (double)lm_base_score(L, ctx, w, st);
+  if (w < 0) lm += L.unk_score_offset;
+  if (eos) lm = lm + (double)lm_base_score(L, st, L.eos, nullptr);
+  if (new_ctx)
+    for (int j = 0; j < L.order - 1; ++j) new_ctx[j] = st[j];
+  return L.alpha * lm * factor + L.beta;
+}
+// score_partial_token: an open word that is no prefix of any unigram costs the unk offset, growing beyond 6 characters
+__device__ __forceinline__ double lm_partial_score(const ssd_lm_tables& L, int node, int plen) {
+  if (plen == 0) return 0.0;
+  double u = node < 0 ? L.unk_score_offset : 0.0;
+  if (plen > 6) u = u * (double)plen / 6.0;
+  return u;
+}
+// set of 64-bit keys in global memory (one per CTA): the closed texts that were scored
+__device__ inline void seen_insert(unsigned long long* tab, unsigned long long mask, uint64_t h) {
+  unsigned long long s = h & mask;
+  for (;;) {
+    const unsigned long long old = atomicCAS(&tab[s], 0ull, (unsigned long long)h);
+    if (old == 0ull || old == (unsigned long long)h) return;
+    s = (s + 1) & mask;
+  }
+}
+__device__ inline bool seen_find(unsigned long long* tab, unsigned long long mask, uint64_t h) {
+  unsigned long long s = h & mask;
+  for (;;) {
+    const unsigned long long k = atomicCAS(&tab[s], 0ull, 0ull);  // an L2 read
+    if (k == (unsigned long long)h) return true;
+    if (k == 0ull) return false;
+    s = (s + 1) & mask;
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
+// LM = false: the no-LM search (the reference's configured path).  LM = true: the same search ranked by acoustic +
+// LM score; every `if constexpr (LM)` block below is absent from the no-LM instantiation.
+template <bool LM>
+__global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
   const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
@@ -456,6 +560,31 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
   unsigned long long* hk_keys = reinterpret_cast<unsigned long long*>(abkt);
   unsigned long long* hk_best = hk_keys + HKS;
   int* hk_idx = reinterpret_cast<int*>(hk_best + HKS);
+  // language-model state of the prefixes (two generations) and the candidates' ranking scores (acoustic + LM)
+  const int CX = lm_ctx_slots(P.lm.order);
+  double* lmt_base = nullptr;   // accumulated LM score of the closed words
+  int* ltrie_base = nullptr;    // trie node of the open word (-1: no unigram starts like it)
+  int* lplen_base = nullptr;    // characters in the open word
+  int* lctx_base = nullptr;     // [W][CX] n-gram ids of the last 1.. order-1 closed words
+  uint64_t* lhw_base = nullptr; // [W][CX] hashes of the 2nd, 3rd, .. last closed words (the last one is Prefix::hl)
+  double* cfused = nullptr;
+  int lm_gs8 = 0, lm_gs4 = 0;
+  if constexpr (LM) {
+    unsigned char* const lp0 = sp;
+    lmt_base = (double*)carve(sp, 8 * WC);
+    ltrie_base = (int*)carve(sp, 4 * WC);
+    lplen_base = (int*)carve(sp, 4 * WC);
+    lctx_base = (int*)carve(sp, 4 * WC * CX);
+    lhw_base = (uint64_t*)carve(sp, 8 * WC * CX);
+    const size_t gb = lm_gen_bytes(WC, P.lm.order);
+    sp = lp0 + 2 * gb;
+    lm_gs8 = (int)(gb / 8);
+    lm_gs4 = (int)(gb / 4);
+    cfused = (double*)carve(sp, 8 * NCAND);
+  }
+  const double* const rscore = LM ? cfused : cscore;  // what ranks and prunes a candidate
+  unsigned long long* const seen = LM ? P.seen + (int64_t)blockIdx.x * P.seen_cap : nullptr;
+  (void)CX; (void)lm_gs4;
 
   const int tid = (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -514,6 +643,23 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       sc->np = 1;
       sc->nodes_used = 1u;
       nodes[0] = make_uint2(0u, 0u);
+      if constexpr (LM) {  // cached_lm_scores = {"": (0, start state <s>)}
+        lmt_base[0] = 0.0;
+        ltrie_base[0] = 0;
+        lplen_base[0] = 0;
+        for (int j = 0; j < CX; ++j) {
+          lctx_base[j] = (j == 0) ? P.lm.bos : -1;
+          lhw_base[j] = 0ull;
+        }
+      }
+    }
+    unsigned long long seen_mask = 0ull;
+    if constexpr (LM) {
+      // at most one new closed text per live prefix and frame; load factor <= 1/2
+      unsigned long long slots = 1024ull;
+      while (slots < 2ull * (unsigned long long)len * (unsigned long long)W && (int64_t)slots < P.seen_cap) slots <<= 1;
+      seen_mask = slots - 1ull;
+      for (unsigned long long i = (unsigned long long)tid; i < slots; i += BM_THREADS) seen[i] = 0ull;
     }
     for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
     for (int i = tid; i < HKS; i += BM_THREADS) {
@@ -598,6 +744,32 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       const FrameRec F = frame_rec(t);
       const int nc1 = sc->nc1[t & 1];
       const int np = sc->np;
+      // LM state of the current (A) and next (N) generation
+      double* const lmtA = LM ? lmt_base + g * lm_gs8 : nullptr;
+      double* const lmtN = LM ? lmt_base + (g ^ 1) * lm_gs8 : nullptr;
+      int* const trieA = LM ? ltrie_base + g * lm_gs4 : nullptr;
+      int* const trieN = LM ? ltrie_base + (g ^ 1) * lm_gs4 : nullptr;
+      int* const plenA = LM ? lplen_base + g * lm_gs4 : nullptr;
+      int* const plenN = LM ? lplen_base + (g ^ 1) * lm_gs4 : nullptr;
+      int* const ctxA = LM ? lctx_base + g * lm_gs4 : nullptr;
+      int* const ctxN = LM ? lctx_base + (g ^ 1) * lm_gs4 : nullptr;
+      uint64_t* const hwA = LM ? lhw_base + g * lm_gs8 : nullptr;
+      uint64_t* const hwN = LM ? lhw_base + (g ^ 1) * lm_gs8 : nullptr;
+      // LM score of a live prefix: closed words + open word
+      auto lm_of = [&](int p) -> double { return lmtA[p] + lm_partial_score(P.lm, trieA[p], plenA[p]); };
+      // history key: (last closed word(s), open word, last char); with an LM the last order-1 closed words count
+      // (`older` = hashes of the 2nd, 3rd, .. last closed word, `shifted`: the entry closes a word, so the prefix's
+      // last word `hl_old` becomes the 2nd last)
+      auto hist_key = [&](uint64_t hl, uint64_t ho, int lc, int p, bool shifted, uint64_t hl_old) -> uint64_t {
+        uint64_t hk = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);  // never 0 (hmix)
+        if constexpr (LM) {
+          for (int j = 0; j + 2 <= CX; ++j) {  // the (j+2)-th last closed word
+            const uint64_t w = shifted ? (j == 0 ? hl_old : hwA[p * CX + j - 1]) : hwA[p * CX + j];
+            hk = hmix(hk ^ w, 0x33u + (uint32_t)j);
+          }
+        }
+        return hk;
+      };
       const unsigned node0 = sc->nodes_used;  // read here: thread 0 rewrites it in phase 6b
       SSD_ASSERT(np >= 1 && np <= W);
 
@@ -630,8 +802,9 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
             lc = (uint32_t)c1;
           }
           newb[p] = v;
+          if constexpr (LM) v += lm_of(p);  // the cut below is on the ranking score
           m = v > m ? v : m;
-          sel_hk[p] = hmix(hmix(A.hl[p] ^ hmix(A.ho[p], 0x5bu), 0xa7u), 0x100u + lc);  // phase 5's key of that entry
+          sel_hk[p] = hist_key(A.hl[p], A.ho[p], (int)lc, p, false, 0ull);  // phase 5's key of that entry
         }
         m = warp_max_d(m);
         if (lane == 0) sc->wmax[warp] = m;
@@ -641,7 +814,8 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         for (int w = 1; w < BM_CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
         const double cut = mm + (double)s_prune;
         for (int p = tid; p < np; p += BM_CONS) {
-          const double v = newb[p];
+          double v = newb[p];
+          if constexpr (LM) v += lm_of(p);
           if (!(v >= cut) || v == -INFINITY) general = true;
           const uint64_t hk = sel_hk[p];
           for (int q = 0; q < np; ++q)
@@ -676,7 +850,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
 #endif
       // ---- phase 1: tot, parent slot.  (When no staircase row is cut -- see phase 2 -- nobody needs another prefix's
       // tot before phase 3 except for the parent's, which is then recomputed on the spot: phases 1 and 2 share a barrier.)
-      const bool cut_rows = nc1 > W / np + 1;
+      const bool cut_rows = !LM && nc1 > W / np + 1;  // under LM scores the staircase bound does not hold: full rows
       for (int p = tid; p < np; p += BM_CONS) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
         par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
@@ -769,11 +943,33 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
             const uint64_t h = hmix(A.H[p], (uint32_t)c);
             if (table_find(tkeys, tvals, tmask, h) < 0)  // else folded into the live child's snb
               s = ((c == e) ? A.sb[p] : tot[p]) + (double)F.rl[c];
+            if constexpr (LM) {
+              // upstream LM-scores every merged beam before pruning: the closed text enters its score cache
+              if (c == space_lbl) seen_insert(seen, seen_mask, h);
+            }
           }
           d = ((uint32_t)p << 8) | (uint32_t)c;
         }
         cscore[k] = s;
         cdesc[k] = d;
+        if constexpr (LM) {
+          if (s != -INFINITY) {
+            const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
+            double lm;
+            if (c == 0 || c == 0xFE) {
+              lm = lm_of(p);
+            } else if (c == space_lbl) {  // closes the open word: score it as a word after the prefix's LM state
+              const int node = trieA[p];
+              lm = lmtA[p] + lm_word_score(P.lm, P.lm_factor, ctxA + p * CX, node >= 0 ? P.lm.trie_word[node] : -1, false, nullptr);
+            } else {
+              const int node = trieA[p];
+              const int child = node >= 0 ? P.lm.trie_child[(int64_t)node * P.lm.n_labels + c] : -1;
+              lm = lmtA[p] + lm_partial_score(P.lm, child, plenA[p] + 1);
+            }
+            s = s + lm;
+          }
+          cfused[k] = s;
+        }
         m_loc = s > m_loc ? s : m_loc;
       }
       m_loc = warp_max_d(m_loc);
@@ -797,7 +993,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         int running = 0;
         for (int base_k = 0; base_k < ncand; base_k += BM_CONS) {
           const int k = base_k + tid;
-          const bool alive = k < ncand && cscore[k] >= cutoff && cscore[k] != -INFINITY;
+          const bool alive = k < ncand && rscore[k] >= cutoff && rscore[k] != -INFINITY;
           const unsigned m = __ballot_sync(FULL, alive);
           if (lane == 0) sc->wcnt[warp] = __popc(m);
           cons_sync();
@@ -836,7 +1032,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         const double top = cutoff - (double)s_prune;
         const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
         for (int i = tid; i < n_alive; i += BM_CONS) {
-          int b = (int)((top - cscore[aidx[i]]) * scale);
+          int b = (int)((top - rscore[aidx[i]]) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
           abkt[i] = b;
           atomicAdd(&hist[b], 1);
@@ -869,11 +1065,11 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         const int m = sc->n_b;
         for (int t = tid; t < m; t += BM_CONS) {
           const int i = blist[t];
-          const double mine = cscore[aidx[i]];
+          const double mine = rscore[aidx[i]];
           int rk = 0;
           for (int u = 0; u < m; ++u) {
             const int j = blist[u];
-            const double o = cscore[aidx[j]];
+            const double o = rscore[aidx[j]];
             rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
           }
           abkt[i] = rk < need ? -1 : 256;  // in / out
@@ -930,15 +1126,16 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
         uint64_t hl = A.hl[p], ho = A.ho[p];
         int lc;
+        bool shifted = false;
         if (c == 0) lc = 0;
         else if (c == 0xFE) lc = A.last[p];
         else {
           lc = c;
-          if (c == space_lbl) { hl = ho; ho = 0ull; }
+          if (c == space_lbl) { hl = ho; ho = 0ull; shifted = true; }
           else ho = hmix(ho, (uint32_t)c);
         }
-        // one 64-bit key for (last word, open word, last char)
-        const uint64_t hk = hmix(hmix(hl ^ hmix(ho, 0x5bu), 0xa7u), 0x100u + (uint32_t)lc);  // never 0 (hmix)
+        // one 64-bit key for (last word(s), open word, last char)
+        const uint64_t hk = hist_key(hl, ho, lc, p, shifted, A.hl[p]);
         sel_hk[r] = hk;
         if (!small_sel) {
           int s_ = (int)(hk & (uint64_t)(HKS - 1));
@@ -947,7 +1144,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
             if (old == 0ull || old == (unsigned long long)hk) break;
             s_ = (s_ + 1) & (HKS - 1);
           }
-          atomicMax(&hk_best[s_], order_key(cscore[sel[r]]));
+          atomicMax(&hk_best[s_], order_key(rscore[sel[r]]));
           sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
         }
       }
@@ -956,7 +1153,7 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
       if (!small_sel) {
         for (int r = tid; r < n_sel; r += BM_CONS) {
           const int s_ = sel_slot[r];
-          if (order_key(cscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
+          if (order_key(rscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
         }
         cons_sync();
       }
@@ -964,11 +1161,11 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         int keep;
         if (small_sel) {
           const uint64_t hk = sel_hk[r];
-          const double mine = cscore[sel[r]];
+          const double mine = rscore[sel[r]];
           keep = 1;
           for (int q = 0; q < n_sel; ++q) {
             if (q == r || sel_hk[q] != hk) continue;
-            const double o = cscore[sel[q]];
+            const double o = rscore[sel[q]];
             if (o > mine || (o == mine && sel[q] < sel[r])) keep = 0;
           }
         } else {
@@ -1034,6 +1231,10 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         N.sb[s] = (keepf[p] & 1) ? newb[p] : neg_inf();
         N.snb[s] = (keepf[p] & 2) ? newnb[p] : neg_inf();
         table_insert(tkeys, tvals, tmask, A.H[p], s);
+        if constexpr (LM) {
+          lmtN[s] = lmtA[p]; trieN[s] = trieA[p]; plenN[s] = plenA[p];
+          for (int j = 0; j < CX; ++j) { ctxN[s * CX + j] = ctxA[p * CX + j]; hwN[s * CX + j] = hwA[p * CX + j]; }
+        }
       }
       for (int r = tid; r < n_sel; r += BM_CONS) {
         const int j = sel_slot[r];
@@ -1053,6 +1254,24 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
         N.node[s] = nd;
         nodes[nd] = make_uint2(A.node[p], (unsigned)c);
         table_insert(tkeys, tvals, tmask, h, s);
+        if constexpr (LM) {
+          if (c == space_lbl) {  // the open word is closed: its score joins the text's, the LM state moves on
+            const int node = trieA[p];
+            int st[LM_CX];
+            lmtN[s] = lmtA[p] + lm_word_score(P.lm, P.lm_factor, ctxA + p * CX, node >= 0 ? P.lm.trie_word[node] : -1, false, st);
+            trieN[s] = 0; plenN[s] = 0;
+            for (int j = 0; j < CX; ++j) {
+              ctxN[s * CX + j] = j < P.lm.order - 1 ? st[j] : -1;
+              hwN[s * CX + j] = j == 0 ? A.hl[p] : hwA[p * CX + j - 1];
+            }
+          } else {
+            const int node = trieA[p];
+            lmtN[s] = lmtA[p];
+            trieN[s] = node >= 0 ? P.lm.trie_child[(int64_t)node * P.lm.n_labels + c] : -1;
+            plenN[s] = plenA[p] + 1;
+            for (int j = 0; j < CX; ++j) { ctxN[s * CX + j] = ctxA[p * CX + j]; hwN[s * CX + j] = hwA[p * CX + j]; }
+          }
+        }
       }
       if (tid == 0) {
         sc->np = n_old + n_new;
@@ -1098,6 +1317,31 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
             f = lse2(f, tot[q]);
             if (q < rep) rep = q;
           }
+        if constexpr (LM) {
+          // upstream's last pass: the open word is closed and scored WITH the end-of-sentence term -- unless the
+          // resulting text is already in its score cache (it was scored as a closed text in some frame), whose
+          // entry has none; texts that end closed are always in the cache.
+          if (rep == p) {
+            const double* lmtF = lmt_base + g * lm_gs8;
+            const int* trieF = ltrie_base + g * lm_gs4;
+            const int* plenF = lplen_base + g * lm_gs4;
+            const int* ctxF = lctx_base + g * lm_gs4;
+            int q_open = -1, q_closed = -1;
+            for (int q = 0; q < np; ++q)
+              if (A.Hstrip[q] == hs) {
+                if (plenF[q] > 0) q_open = q; else q_closed = q;
+              }
+            double lm;
+            if (q_open >= 0) {
+              const bool cached = space_lbl >= 0 && seen_find(seen, seen_mask, hmix(A.H[q_open], (uint32_t)space_lbl));
+              const int node = trieF[q_open];
+              lm = lmtF[q_open] + lm_word_score(P.lm, P.lm_factor, ctxF + q_open * CX, node >= 0 ? P.lm.trie_word[node] : -1, !cached, nullptr);
+            } else {
+              lm = lmtF[q_closed];
+            }
+            f = f + lm;
+          }
+        }
         newb[p] = (rep == p) ? f : neg_inf();  // one representative per group competes
       }
       cons_sync();
@@ -1126,15 +1370,16 @@ __global__ void __launch_bounds__(BM_THREADS, SSD_BEAM_MINCTAS) beam_kernel(cons
 }
 
 // ------------------------------------------------------------------ host side
-static int beam_grid(int64_t B, size_t smem) {
+static int beam_grid(int64_t B, size_t smem, bool lm) {
 #ifdef SSD_EMU
-  (void)smem;
+  (void)smem; (void)lm;
   return (int)(B < 3 ? B : 3);
 #else
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, BM_THREADS, smem);
+  if (lm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<true>, BM_THREADS, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<false>, BM_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   const int64_t g = (int64_t)sms * per_sm;
   return (int)(B < g ? B : g);
@@ -1159,12 +1404,12 @@ static int beam_max_grid() {
 // Resident CTAs of a launch over `items` work items at capacity `width`: what the occupancy calculator gives for the
 // launch's shared-memory footprint, never more than there are items.  The workspace is sized from the same number
 // (the footprint is taken with the smaller of the two possible label counts, so it can only over-estimate the grid).
-static int beam_grid_for(int64_t items, int64_t V, int VL, int width, size_t* smem_out) {
-  const int TS = beam_table_slots(width), NCAND = beam_ncand_cap(width, VL);
-  const size_t smem = beam_smem_bytes(width, (int)V, VL, TS, NCAND);
+static int beam_grid_for(int64_t items, int64_t V, int VL, int width, size_t* smem_out, int lm_order = 0) {
+  const int TS = beam_table_slots(width), NCAND = lm_order > 0 ? beam_ncand_cap_lm(width, VL) : beam_ncand_cap(width, VL);
+  const size_t smem = beam_smem_bytes(width, (int)V, VL, TS, NCAND, lm_order);
   if (smem_out) *smem_out = smem;
   if (smem > 227 * 1024) return 0;
-  int grid = beam_grid(items, smem);
+  int grid = beam_grid(items, smem, lm_order > 0);
   const int gmax = beam_max_grid();
   return grid > gmax ? gmax : grid;
 }
@@ -1175,11 +1420,35 @@ size_t beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int width) {
   return 256 + (size_t)g * (size_t)beam_node_cap(T, width) * sizeof(uint2);
 }
 
+// slots of one CTA's set of scored closed texts: a power of two >= 2 * T * W
+static int64_t beam_seen_cap(int64_t T, int W) {
+  int64_t n = 1024;
+  while (n < 2 * T * (int64_t)W) n <<= 1;
+  return n;
+}
+static size_t beam_nodes_bytes(int grid, int64_t T, int W) {
+  return ((size_t)grid * (size_t)beam_node_cap(T, W) * sizeof(uint2) + 255) & ~(size_t)255;
+}
+// LM launches: [counter 256 B | back-pointer nodes | scored-text sets]; the grid is bounded with the smallest
+// per-prefix LM state (order 1), which can only over-estimate it
+size_t beam_lm_workspace_bytes(int64_t B, int64_t T, int64_t V, int width) {
+  int g = beam_grid_for(B, V, (int)V - 1, width, nullptr, 1);
+  if (g < 1) g = 1;
+  return 256 + beam_nodes_bytes(g, T, width) + (size_t)g * (size_t)beam_seen_cap(T, width) * sizeof(unsigned long long);
+}
+
 int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths,
                 const int32_t* order, int blank, int pad, int space, const ssd_beam_setting* settings, int n_set,
-                int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                const ssd_lm_tables* lm, int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
   if (B == 0 || n_set == 0) return SSD_OK;
   BeamParams P;
+  P.lm = ssd_lm_tables();
+  P.lm_factor = 1.0 / std::log10(std::exp(1.0));
+  P.seen = nullptr;
+  P.seen_cap = 0;
+  if (lm) P.lm = *lm;
+  const int lm_order = lm ? lm->order : 0;
   P.lp = lp; P.T = T; P.sb = sb; P.st = st; P.B = (int)B; P.V = (int)V;
   P.lengths = lengths; P.order = order;
   P.blank = blank; P.pad = (pad >= 0 && pad < V) ? pad : -1; P.space = space;
@@ -1200,27 +1469,39 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   P.out_tok = out_tok; P.out_len = out_len; P.out_score = out_score;
   P.VL = beam_vl(V, blank, P.pad);
   P.TS = beam_table_slots(width);
-  P.NCAND = beam_ncand_cap(width, P.VL);
+  P.NCAND = lm ? beam_ncand_cap_lm(width, P.VL) : beam_ncand_cap(width, P.VL);
+  if (lm && lm->n_labels != P.VL)
+    return fail(SSD_ERR_BAD_ARG, "beam: the LM's character trie is laid out for %d labels, the decoder has %d", lm->n_labels, P.VL);
   P.use_tma = (st == V) && aligned16(lp) && ((sb * 4) % 16 == 0) && ((V * 4) % 16 == 0) ? 1 : 0;
   size_t smem = 0;
-  const int grid = beam_grid_for(B * n_set, V, P.VL, width, &smem);
+  const int grid = beam_grid_for(B * n_set, V, P.VL, width, &smem, lm_order);
   if (grid < 1) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
 #ifndef SSD_EMU
-  cudaError_t e = cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = lm ? cudaFuncSetAttribute(beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
 #endif
   P.node_cap = beam_node_cap(T, width);
-  const size_t need = 256 + (size_t)grid * (size_t)P.node_cap * sizeof(uint2);
+  size_t need = 256 + (size_t)grid * (size_t)P.node_cap * sizeof(uint2);
+  if (lm) {
+    P.seen_cap = beam_seen_cap(T, width);
+    need = 256 + beam_nodes_bytes(grid, T, width) + (size_t)grid * (size_t)P.seen_cap * sizeof(unsigned long long);
+  }
   if (!ws || ws_bytes < need) return fail(SSD_ERR_WORKSPACE, "beam: workspace %zu bytes, need %zu", ws_bytes, need);
   P.counter = reinterpret_cast<unsigned*>(ws);
   P.nodes = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(ws) + 256);
+  if (lm) P.seen = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + 256 + beam_nodes_bytes(grid, T, width));
 #ifdef SSD_EMU
   *P.counter = 0u;
 #else
   e = cudaMemsetAsync(P.counter, 0, 256, stream);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaMemsetAsync: %s", cudaGetErrorString(e));
 #endif
-  SSD_LAUNCH(beam_kernel, (unsigned)grid, BM_THREADS, smem, stream, P);
+  if (lm) {
+    SSD_LAUNCH(beam_kernel<true>, (unsigned)grid, BM_THREADS, smem, stream, P);
+  } else {
+    SSD_LAUNCH(beam_kernel<false>, (unsigned)grid, BM_THREADS, smem, stream, P);
+  }
   return check_launch("beam_kernel");
 }
 

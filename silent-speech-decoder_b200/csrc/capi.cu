@@ -55,7 +55,7 @@ int ssd_ctc_beam(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_
   if (!(beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam: beam_prune_logp must be <= 0");
   ssd_beam_setting one;
   one.beam_width = beam_width; one.beam_prune_logp = beam_prune_logp; one.blank_bias = blank_bias; one.token_min_logp = token_min_logp;
-  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, &one, 1, out_tokens, out_lengths,
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, &one, 1, nullptr, out_tokens, out_lengths,
                      out_scores, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -76,7 +76,47 @@ int ssd_ctc_beam_grid(const float* log_probs, int64_t B, int64_t T, int64_t V, i
       return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_grid: settings[%d].beam_width=%d outside [1,%d]", i, settings[i].beam_width, SSD_MAX_BEAM);
     if (!(settings[i].beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_grid: settings[%d].beam_prune_logp must be <= 0", i);
   }
-  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, settings, n_settings, out_tokens,
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, settings, n_settings, nullptr, out_tokens,
+                     out_lengths, out_scores, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+uint64_t ssd_lm_hash(uint64_t key) {
+  const uint64_t h = key * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+
+size_t ssd_ctc_beam_lm_workspace_bytes(int64_t B, int64_t T, int64_t V, int beam_width) {
+  if (B <= 0 || T < 0 || V <= 0 || beam_width <= 0) return 256;
+  return beam_lm_workspace_bytes(B, T, V, beam_width);
+}
+
+int ssd_ctc_beam_lm(const float* log_probs, int64_t B, int64_t T, int64_t V, int64_t stride_b, int64_t stride_t,
+                    const int64_t* lengths, const int32_t* order, int blank, int pad, int space,
+                    const ssd_beam_setting* settings, int n_settings, const ssd_lm_tables* lm, int32_t* out_tokens,
+                    int32_t* out_lengths, double* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("ssd_ctc_beam_lm", log_probs, B, T, V, stride_b, stride_t);
+  if (rc) return rc;
+  if (n_settings < 0 || n_settings > SSD_MAX_BEAM_SETTINGS)
+    return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_lm: n_settings=%d outside [0,%d]", n_settings, SSD_MAX_BEAM_SETTINGS);
+  if (n_settings > 0 && !settings) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: settings is NULL");
+  if (B > 0 && n_settings > 0 && (!lengths || !out_lengths || (T > 0 && !out_tokens))) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: NULL lengths/output pointer");
+  if (blank < 0 || blank >= V) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: blank=%d outside [0,%lld)", blank, (long long)V);
+  if (B * (int64_t)(n_settings > 0 ? n_settings : 1) > 2147483647LL) return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_lm: B * n_settings exceeds 32-bit range");
+  for (int i = 0; i < n_settings; ++i) {
+    if (settings[i].beam_width < 1 || settings[i].beam_width > SSD_MAX_BEAM)
+      return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_lm: settings[%d].beam_width=%d outside [1,%d]", i, settings[i].beam_width, SSD_MAX_BEAM);
+    if (!(settings[i].beam_prune_logp <= 0.f)) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: settings[%d].beam_prune_logp must be <= 0", i);
+  }
+  if (!lm) return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: lm is NULL (ssd_ctc_beam_grid is the no-LM entry)");
+  if (lm->order < 1 || lm->order > SSD_MAX_LM_ORDER)
+    return fail(SSD_ERR_UNSUPPORTED, "ssd_ctc_beam_lm: LM order %d outside [1,%d]", lm->order, SSD_MAX_LM_ORDER);
+  if (!lm->trie_child || !lm->trie_word || !lm->ngram_keys || !lm->ngram_vals || !lm->ngram_prob || !lm->ngram_backoff)
+    return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: NULL table pointer in ssd_lm_tables");
+  if (lm->n_trie_nodes < 1 || lm->n_ngrams < 1 || (lm->ngram_mask & (lm->ngram_mask + 1)) != 0)
+    return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: empty tables or ngram_mask + 1 not a power of two");
+  if (lm->bos >= lm->n_ngrams || lm->eos >= lm->n_ngrams || lm->unk >= lm->n_ngrams)
+    return fail(SSD_ERR_BAD_ARG, "ssd_ctc_beam_lm: special word id outside the n-gram table");
+  return beam_launch(log_probs, B, T, V, stride_b, stride_t, lengths, order, blank, pad, space, settings, n_settings, lm, out_tokens,
                      out_lengths, out_scores, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -32,9 +32,12 @@ int greedy_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, 
                   float bias, int32_t* out_tok, int32_t* out_len, cudaStream_t stream);
 
 size_t beam_workspace_bytes(int64_t B, int64_t T, int64_t V, int width);
+size_t beam_lm_workspace_bytes(int64_t B, int64_t T, int64_t V, int width);
+// lm == nullptr: the no-LM search
 int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* lengths,
                 const int32_t* order, int blank, int pad, int space, const ssd_beam_setting* settings, int n_set,
-                int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes, cudaStream_t stream);
+                const ssd_lm_tables* lm, int32_t* out_tok, int32_t* out_len, double* out_score, void* ws, size_t ws_bytes,
+                cudaStream_t stream);
 
 size_t loss_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t S_max);
 size_t loss_fallback_counter_offset(int64_t B, int64_t T, int64_t V, int64_t S_max);

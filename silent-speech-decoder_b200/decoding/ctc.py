@@ -193,14 +193,35 @@ def build_beam_decoder(
     beam_prune_logp: float = -10.0,
     blank_bias: float = 0.0,
 ) -> DecoderFn:
-    if lm_path:
-        raise NotImplementedError(
-            "language-model fusion is outside the native CTC hot path (lm_path must be None); "
-            "alpha/beta have no effect without an LM, exactly as in pyctcdecode"
-        )
-    del alpha, beta  # inert without an LM (ctc.py:67-72)
     text, space = _beam_label_strings(vocab)
     pad = vocab.pad_id if (vocab.pad_id != vocab.blank_id and 0 <= vocab.pad_id < vocab.size) else -1
+    if lm_path:
+        # ctc.py:67-72: build_ctcdecoder(labels, kenlm_model_path=str(lm_path), alpha, beta) -- word n-gram fusion
+        # (scope row f-4).  The ARPA file becomes device tables once, here; every call then runs ssd_ctc_beam_lm.
+        from .lm import build_tables
+
+        if not str(lm_path).endswith(".arpa"):
+            raise ValueError(f"lm_path must be an ARPA text file (what build_char_lm.py writes); got {lm_path}")
+        keep = [i for i in range(vocab.size) if i not in {vocab.blank_id, vocab.pad_id}]
+        tables = build_tables(lm_path, [""] + [text[i] for i in keep], alpha=alpha, beta=beta)
+
+        def decode_lm(log_probs: torch.Tensor, lengths: torch.Tensor) -> List[str]:
+            if log_probs.dim() == 3 and log_probs.size(-1) != vocab.size:
+                raise ValueError(
+                    f"Input logits shape is {tuple(log_probs.shape[1:])}, but vocabulary is size {vocab.size}"
+                )
+
+            def launch(x, n):
+                tok, cnt, _ = ops.beam_lm_ids(x, n, vocab.blank_id, pad, space, tables,
+                                              [(beam_width, beam_prune_logp, blank_bias, -5.0)])
+                return tok[0], cnt[0]
+
+            return _pipelined(log_probs, lengths, launch,
+                              lambda tok, cnt: _rows_to_strings(tok, cnt, text, normalise_space=True))
+
+        decode_lm.lm_tables = tables  # for callers that want the scores (ops.beam_lm_ids)
+        return decode_lm
+    del alpha, beta  # inert without an LM (ctc.py:67-72)
 
     def decode(log_probs: torch.Tensor, lengths: torch.Tensor) -> List[str]:
         if log_probs.dim() == 3 and log_probs.size(-1) != vocab.size:

@@ -164,12 +164,12 @@ class DecoderSetting:
             "beta": (0.0 if self.beta is None else self.beta) if beam else None,
             "beam_prune_logp": (-10.0 if self.beam_prune_logp is None else self.beam_prune_logp) if beam else None,
             "blank_bias": float(self.blank_bias),
-            "lm_path": None,
+            "lm_path": str(self.lm_path) if (beam and self.use_lm and self.lm_path) else None,  # evaluate.py:316
         }
 
     def build(self, vocab: Vocab) -> DecoderFn:
         r = self.resolved()
-        return build_decoder(method=self.method, vocab=vocab, lm_path=None, beam_width=int(r["beam_width"] or 50),
+        return build_decoder(method=self.method, vocab=vocab, lm_path=r["lm_path"], beam_width=int(r["beam_width"] or 50),
                              alpha=float(r["alpha"] or 0.0), beta=float(r["beta"] or 0.0),
                              beam_prune_logp=float(-10.0 if r["beam_prune_logp"] is None else r["beam_prune_logp"]),
                              blank_bias=float(self.blank_bias))
@@ -181,8 +181,9 @@ class GridEvaluator:
     (setting, utterance)); greedy settings take one greedy launch each.  The reference runs its whole evaluation --
     encoder included -- once per setting (``orchestrate.py:129-153,235-249``).
 
-    Settings that ask for a language model are reported under ``skipped`` (the LM is outside this path; the
-    reference skips them too when the ARPA file is missing, ``orchestrate.py:117-119``)."""
+    Settings that ask for a language model run through the LM-fused kernel (``ssd_ctc_beam_lm``, one launch per
+    setting: alpha and beta belong to the tables) when their ARPA file exists, and are reported under ``skipped``
+    when it does not -- what the reference does (``orchestrate.py:117-119,428``)."""
 
     MAX_PER_LAUNCH = 8  # SSD_MAX_BEAM_SETTINGS
 
@@ -193,8 +194,11 @@ class GridEvaluator:
         if len(set(names)) != len(names):
             raise ValueError(f"decoder setting names must be unique: {names}")
         self.vocab = vocab
-        self.skipped = [g.name for g in grid if g.use_lm]
-        self.settings = [g for g in grid if not g.use_lm]
+        def lm_missing(g):
+            return g.use_lm and not (g.lm_path and Path(g.lm_path).exists())
+
+        self.skipped = [g.name for g in grid if lm_missing(g)]
+        self.settings = [g for g in grid if not lm_missing(g)]
         self.evaluators: Dict[str, Evaluator] = {g.name: Evaluator(g.build(vocab), g.resolved()) for g in self.settings}
         self._beam_text, self._space = _ctc._beam_label_strings(vocab)
         self._pad = vocab.pad_id if (vocab.pad_id != vocab.blank_id and 0 <= vocab.pad_id < vocab.size) else -1
@@ -206,7 +210,10 @@ class GridEvaluator:
         ln = torch.as_tensor(lengths).to(dev, non_blocking=True)
         ids = list(utterance_ids)
         out: Dict[str, List[str]] = {}
-        beams = [g for g in self.settings if g.method.lower() == "beam"]
+        beams = [g for g in self.settings if g.method.lower() == "beam" and not g.use_lm]
+        for g in self.settings:
+            if g.method.lower() == "beam" and g.use_lm:  # the decoder built for it holds the LM's device tables
+                out[g.name] = self.evaluators[g.name].add(ids, transcripts, lp, ln)
         for lo in range(0, len(beams), self.MAX_PER_LAUNCH):
             part = beams[lo: lo + self.MAX_PER_LAUNCH]
             spec = []

@@ -180,6 +180,52 @@ def beam_grid_ids(
     return tok, cnt, score
 
 
+def beam_lm_ids(
+    log_probs: torch.Tensor,
+    lengths: torch.Tensor,
+    blank: int,
+    pad: int,
+    space: int,
+    lm,
+    settings: Sequence[Tuple[int, float, float, float]],
+    sort_by_length: bool = True,
+):
+    """LM-fused prefix beam search (``ssd_ctc_beam_lm``): ``lm`` is a ``decoding.lm.LanguageModelTables``; ``settings``
+    as in ``beam_grid_ids``.  -> (tokens int32 (n,B,T), counts int32 (n,B), ranking scores float64 (n,B)) on the device."""
+    import ctypes
+
+    lib = _native.load()
+    dev = _device(log_probs)
+    n = len(settings)
+    if n > 8:
+        raise ValueError(f"at most 8 decoder settings per launch; got {n}")
+    with torch.cuda.device(dev):
+        x = _prep_log_probs(log_probs, dev)
+        B, T, V = x.shape
+        ln = _prep_lengths(lengths, B, dev)
+        tok = torch.empty((n, B, max(T, 1)), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((n, B), dtype=torch.int32, device=dev)
+        score = torch.zeros((n, B), dtype=torch.float64, device=dev)
+        if B and T and n:
+            sb, st = _strides(x)
+            perm = sorted(range(n), key=lambda i: -int(settings[i][0]))
+            arr = (_native.BeamSetting * n)(*[_native.BeamSetting(int(settings[i][0]), float(settings[i][1]), float(settings[i][2]),
+                                                                   float(settings[i][3])) for i in perm])
+            order = torch.argsort(ln, descending=True, stable=True).to(torch.int32) if (sort_by_length and B > 1) else None
+            wmax = max(int(s[0]) for s in settings)
+            ws = _workspace(dev, "beam_lm", int(lib.ssd_ctc_beam_lm_workspace_bytes(B * n, T, V, wmax)))
+            tables = lm.struct_for(dev)
+            lib.check(lib.ssd_ctc_beam_lm(x.data_ptr(), B, T, V, sb, st, ln.data_ptr(),
+                                          order.data_ptr() if order is not None else None, int(blank), int(pad), int(space),
+                                          ctypes.cast(arr, ctypes.c_void_p), n, ctypes.addressof(tables), tok.data_ptr(),
+                                          cnt.data_ptr(), score.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+            LAUNCHES["beam"] += 1
+            if perm != list(range(n)):
+                inv = torch.tensor([perm.index(i) for i in range(n)], device=dev)
+                tok, cnt, score = tok[inv], cnt[inv], score[inv]
+    return tok, cnt, score
+
+
 def row_logsumexp(x: torch.Tensor) -> torch.Tensor:
     """(B,T,V) fp32 -> (B,T) fp32 log sum_v exp(x) on the device (``ssd_row_logsumexp``)."""
     lib = _native.load()

@@ -105,6 +105,33 @@ def beam_grid(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, se
     return [([[int(x) for x in tok[i, b, : cnt[i, b]]] for b in range(B)], sc[i]) for i in range(n)]
 
 
+def beam_lm(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, tables, settings, order=None):
+    """LM-fused search on host arrays: ``tables`` = decoding.lm.LanguageModelTables (numpy side only).
+    -> per setting (ids, ranking scores)."""
+    import ctypes as C
+
+    from silent_speech_decoder_b200._native import BeamSetting, LmTables
+
+    lp = np.ascontiguousarray(lp, dtype=np.float32)
+    B, T, V = lp.shape
+    n = len(settings)
+    ln = np.asarray(lengths, dtype=np.int64)
+    tok = np.full((n, B, max(T, 1)), -7, dtype=np.int32)
+    cnt = np.full((n, B), -7, dtype=np.int32)
+    sc = np.full((n, B), np.nan, dtype=np.float64)
+    arr = (BeamSetting * max(n, 1))(*[BeamSetting(int(w), float(p), float(b), float(t)) for w, p, b, t in settings])
+    wmax = max([int(s[0]) for s in settings], default=1)
+    ws = np.zeros(lib.ssd_ctc_beam_lm_workspace_bytes(B * max(n, 1), T, V, wmax) // 8 + 1, dtype=np.int64)
+    od = None if order is None else np.asarray(order, dtype=np.int32)
+    held = [np.ascontiguousarray(a) for a in (tables.trie_child, tables.trie_word, tables.ngram_keys, tables.ngram_vals,
+                                              tables.ngram_prob, tables.ngram_backoff)]
+    st = LmTables(*[_ptr(a) for a in held], len(tables.ngram_keys) - 1, held[0].shape[0], held[0].shape[1], held[4].shape[0],
+                  tables.order, tables.bos, tables.eos, tables.unk, 0, tables.alpha, tables.beta, tables.unk_score_offset)
+    lib.check(lib.ssd_ctc_beam_lm(_ptr(lp), B, T, V, T * V, V, _ptr(ln), _ptr(od), blank, pad, space, C.cast(arr, C.c_void_p), n,
+                                  C.addressof(st), _ptr(tok), _ptr(cnt), _ptr(sc), _ptr(ws), ws.nbytes, None))
+    return [([[int(x) for x in tok[i, b, : cnt[i, b]]] for b in range(B)], sc[i]) for i in range(n)]
+
+
 def row_lse(lib, x: np.ndarray):
     x = np.ascontiguousarray(x, dtype=np.float32)
     B, T, V = x.shape

@@ -60,8 +60,8 @@ def test_no_cpu_fallback():
         ctc.build_decoder("beam", v)(lp, torch.tensor([4]))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         CTCLoss(blank=1)(lp.transpose(0, 1), torch.tensor([[2, 3]]), torch.tensor([4]), torch.tensor([2]))
-    with pytest.raises(NotImplementedError):
-        ctc.build_decoder("beam", v, lm_path="x.arpa")
+    with pytest.raises(FileNotFoundError):  # an LM path is honoured (row f-4): a missing file is an error, not ignored
+        ctc.build_decoder("beam", v, lm_path="no_such_file.arpa")
 
 
 def test_missing_library_is_an_error(monkeypatch, tmp_path):

@@ -127,8 +127,8 @@ def test_beam_edges():
     lp[2, 3:, V.pad_id] = 0.0                      # pad mass behaves as blank
     assert dec(lp, torch.tensor([6, 6, 6])) == [ob.UNK_GLYPH, "", "a"]
     assert dec(lp, torch.tensor([0, 0, 0])) == ["", "", ""]
-    with pytest.raises(NotImplementedError):
-        ctc.build_decoder("beam", V, lm_path="lm.arpa")
+    with pytest.raises(FileNotFoundError):
+        ctc.build_decoder("beam", V, lm_path="no_such_lm.arpa")
     with pytest.raises(ValueError):
         dec(torch.zeros(1, 4, 47), torch.tensor([4]))
 

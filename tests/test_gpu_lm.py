@@ -1,0 +1,144 @@
+"""Scope row f-4 on the GPU: ssd_ctc_beam_lm (through ops / build_decoder) against oracle/lm.py + oracle/beam.py
+(UNPINNED restatements of kenlm / pyctcdecode; no upstream library or LM-beam vector exists in the reference)."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beam as ob
+from oracle import lm as olm
+from silent_speech_decoder_b200 import ops, synth
+from silent_speech_decoder_b200.data.vocab import Vocab
+from silent_speech_decoder_b200.decoding import ctc
+from silent_speech_decoder_b200.decoding import lm as plm
+from tests import lm_cases
+
+pytestmark = pytest.mark.gpu
+V = Vocab.default()
+TEXT, SPACE = ctc._beam_label_strings(V)
+KEEP = [i for i in range(V.size) if i not in {V.blank_id, V.pad_id}]
+LABEL_TEXT = [""] + [TEXT[i] for i in KEEP]
+SCORE_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def arpas(tmp_path_factory):
+    d = tmp_path_factory.mktemp("lm")
+    out = {}
+    for order in (2, 3, 5):
+        out[order] = str(d / f"w{order}.arpa")
+        lm_cases.write_lm(out[order], order=order, seed=order)
+    return out
+
+
+def _sentences(n, seed):
+    rng = np.random.default_rng(seed)
+    pool = lm_cases.corpus(200, seed=seed + 100) + lm_cases.SENTENCES
+    out = []
+    for _ in range(n):
+        s = pool[int(rng.integers(len(pool)))]
+        if rng.random() < 0.3:  # an out-of-vocabulary word in the middle
+            w = s.split()
+            w.insert(int(rng.integers(len(w) + 1)), "".join(rng.choice(list("abcdefgxyz"), size=int(rng.integers(2, 9)))))
+            s = " ".join(w)
+        out.append(s[:40].strip())
+    return out
+
+
+@pytest.mark.parametrize("order,width,prune,bias,alpha,beta,boost", [
+    (3, 50, -10.0, 0.0, 0.6, 0.0, 3.0),      # the reference's defaults (ctc.py:47-55) with an LM
+    (5, 50, -10.0, 0.0, 0.6, 0.0, 5.0),      # the file build_char_lm.py writes: order 5
+    (5, 100, -12.0, 0.1, 0.9, 1.5, 3.0),     # config_builder.py grid corners
+    (2, 20, -10.0, 0.2, 0.3, 0.5, 4.0),
+    (3, 1, -10.0, 0.0, 0.6, 0.0, 3.0),
+])
+def test_lm_beam_vs_oracle(arpas, order, width, prune, bias, alpha, beta, boost):
+    sents = _sentences(24, seed=order * 100 + width)
+    T = 110
+    lp, _ = lm_cases.spelled_log_probs(sents, T, seed=width + order, boost=boost)
+    ln = synth.ragged_lengths(len(sents), T, 3).tolist()
+    ln[0] = T
+    L = olm.LanguageModel(olm.ArpaModel(arpas[order]), alpha=alpha, beta=beta)
+    want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, blank_bias=bias, lm=L).decode_with_lm_scores(lp, ln)
+    tab = plm.build_tables(arpas[order], LABEL_TEXT, alpha, beta)
+    pad = V.pad_id
+    tok, cnt, score = ops.beam_lm_ids(torch.from_numpy(lp), torch.tensor(ln), V.blank_id, pad, SPACE, tab,
+                                      [(width, prune, bias, -5.0)])
+    got = ctc._rows_to_strings(tok[0], cnt[0], TEXT, normalise_space=True)
+    assert got == [w[0] for w in want]
+    assert np.abs(score[0].cpu().numpy() - np.asarray([w[2] for w in want])).max() <= SCORE_ATOL
+
+
+def test_build_decoder_with_lm_path(arpas):
+    """The reference's call: build_decoder("beam", vocab, lm_path=..., alpha=..., beta=...) (ctc.py:102-121)."""
+    sents = _sentences(12, seed=9)
+    lp, _ = lm_cases.spelled_log_probs(sents, 100, seed=5)
+    ln = [100] * len(sents)
+    dec = ctc.build_decoder("beam", V, lm_path=arpas[3], beam_width=30, alpha=0.7, beta=0.4)
+    L = olm.LanguageModel(olm.ArpaModel(arpas[3]), alpha=0.7, beta=0.4)
+    want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 30, -10.0, lm=L)(lp, ln)
+    assert dec(torch.from_numpy(lp), torch.tensor(ln)) == want
+    assert dec(torch.from_numpy(lp).cuda(), torch.tensor(ln).cuda()) == want
+    no_lm = ctc.build_decoder("beam", V, beam_width=30)(torch.from_numpy(lp), torch.tensor(ln))
+    assert no_lm != want  # the LM matters on this input
+
+
+def test_lm_grid_and_zero_weight_equivalence(arpas):
+    """Several settings in one LM launch; and with alpha = beta = unk offset = 0 at order 2 the LM kernel (full proposal
+    rows) reproduces the no-LM kernel (staircase rows) bit for bit in text, to rounding in score."""
+    lp = torch.cat([synth.flat(6, 120, 5), synth.peaked(6, 120, 6)])
+    ln = synth.ragged_lengths(12, 120, 4)
+    tab = plm.build_tables(arpas[2], LABEL_TEXT, 0.0, 0.0, unk_score_offset=0.0)
+    settings = [(50, -10.0, 0.0, -5.0), (20, -12.0, 0.1, -5.0), (100, -10.0, 0.0, -5.0)]
+    tok, cnt, score = ops.beam_lm_ids(lp, ln, V.blank_id, V.pad_id, SPACE, tab, settings)
+    tok0, cnt0, score0 = ops.beam_grid_ids(lp, ln, V.blank_id, V.pad_id, SPACE, settings)
+    for i in range(len(settings)):
+        assert ctc._rows_to_lists(tok[i], cnt[i]) == ctc._rows_to_lists(tok0[i], cnt0[i])
+    np.testing.assert_allclose(score.cpu().numpy(), score0.cpu().numpy(), rtol=0, atol=1e-9)
+
+
+def test_lm_beam_config3_shape_runs(arpas):
+    """Config-3-sized input (T=500) through the LM kernel: sanity of the workspace sizing and a timing for DESIGN.md."""
+    B, T = 512, 500
+    lp, tg, tl = synth.peaked_aligned(B, T, 11, label_weights=synth.english_label_weights(V.tokens))
+    ln = torch.full((B,), T)
+    tab = plm.build_tables(arpas[5], LABEL_TEXT, 0.6, 0.0)
+    x = lp.cuda()
+    ops.beam_lm_ids(x, ln, V.blank_id, V.pad_id, SPACE, tab, [(50, -10.0, 0.0, -5.0)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tok, cnt, score = ops.beam_lm_ids(x, ln, V.blank_id, V.pad_id, SPACE, tab, [(50, -10.0, 0.0, -5.0)])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"\n[lm beam-50] {B} utterances x T={T}: {dt * 1e3:.1f} ms = {B / dt:.0f} utterances/s")
+    assert torch.isfinite(score).all() and (cnt > 0).all()
+    # spot-check three utterances against the oracle
+    L = olm.LanguageModel(olm.ArpaModel(arpas[5]), alpha=0.6, beta=0.0)
+    dec = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 50, -10.0, lm=L)
+    for b in (0, 200, 511):
+        want = dec.decode_with_lm_scores(lp[b : b + 1].numpy(), [T])[0]
+        got = ctc._rows_to_strings(tok[0, b : b + 1], cnt[0, b : b + 1], TEXT, normalise_space=True)[0]
+        assert got == want[0] and abs(float(score[0, b]) - want[2]) <= SCORE_ATOL
+
+
+def test_grid_evaluator_runs_lm_settings(arpas, tmp_path):
+    """config_builder.py:84,92 put a beam50_lm point in every decoder grid; orchestrate.py:117-119 skips it only when the
+    ARPA file is missing.  Here it runs (LM kernel) next to the no-LM points (one grid launch) over the same batch."""
+    from silent_speech_decoder_b200.evaluation import evaluate as ev
+
+    grid = [ev.DecoderSetting(name="beam50", method="beam", beam_width=50, alpha=0.5, beta=0.0, beam_prune_logp=-12.0, blank_bias=0.1),
+            ev.DecoderSetting(name="beam50_lm", method="beam", beam_width=50, alpha=0.6, beta=0.2, use_lm=True, lm_path=arpas[5]),
+            ev.DecoderSetting(name="beam20_lm_missing", method="beam", beam_width=20, use_lm=True, lm_path=str(tmp_path / "none.arpa"))]
+    g = ev.GridEvaluator(V, grid)
+    assert g.skipped == ["beam20_lm_missing"]
+    sents = _sentences(10, seed=21)
+    lp, _ = lm_cases.spelled_log_probs(sents, 100, seed=8)
+    ln = [100] * len(sents)
+    got = g.add(range(len(sents)), sents, torch.from_numpy(lp), torch.tensor(ln))
+    L = olm.LanguageModel(olm.ArpaModel(arpas[5]), alpha=0.6, beta=0.2)
+    assert got["beam50_lm"] == ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 50, -10.0, lm=L)(lp, ln)
+    assert got["beam50"] == ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 50, -12.0, 0.1)(lp, ln)
+    m = g.finish()
+    assert m["beam50_lm"]["decoder"]["lm_path"] == arpas[5] and m["beam50"]["decoder"]["lm_path"] is None
+    assert m["beam50_lm"]["wer"] < m["beam50"]["wer"]  # the LM earns its keep on noisy spellings of dictionary words

@@ -1,0 +1,249 @@
+"""Scope row f-4, CPU tier: the LM-fusion oracle (oracle/lm.py, oracle/beam.py -- UNPINNED restatements of kenlm /
+pyctcdecode), the host-side table builder (decoding/lm.py) and the LM kernel's logic run on the SIMT emulator."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import beam as ob
+from oracle import lm as olm
+from silent_speech_decoder_b200.data.vocab import Vocab
+from silent_speech_decoder_b200.decoding import ctc
+from silent_speech_decoder_b200.decoding import lm as plm
+from tests import lm_cases
+from tests.emu import harness
+
+V = Vocab.default()
+TEXT, SPACE = ctc._beam_label_strings(V)
+KEEP = [i for i in range(V.size) if i not in {V.blank_id, V.pad_id}]
+LABEL_TEXT = [""] + [TEXT[i] for i in KEEP]
+
+HAND_ARPA = """\\data\\
+ngram 1=6
+ngram 2=5
+ngram 3=2
+
+\\1-grams:
+-1.0\t<unk>\t0
+-99\t<s>\t-0.5
+-0.8\t</s>\t0
+-0.6\ta\t-0.3
+-0.7\tb\t-0.2
+-0.9\tc\t0
+
+\\2-grams:
+-0.4\t<s> a\t-0.25
+-0.5\ta b\t-0.125
+-0.3\tb a\t0
+-0.2\tb </s>\t0
+-0.6\ta </s>\t0
+
+\\3-grams:
+-0.1\t<s> a b
+-0.05\ta b </s>
+
+\\end\\
+"""
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return harness.library()
+
+
+@pytest.fixture(scope="module")
+def hand(tmp_path_factory):
+    p = tmp_path_factory.mktemp("lm") / "hand.arpa"
+    p.write_text(HAND_ARPA)
+    return str(p)
+
+
+@pytest.fixture(scope="module")
+def arpa3(tmp_path_factory):
+    p = tmp_path_factory.mktemp("lm") / "w3.arpa"
+    lm_cases.write_lm(str(p), order=3, seed=0)
+    return str(p)
+
+
+@pytest.fixture(scope="module")
+def arpa5(tmp_path_factory):
+    p = tmp_path_factory.mktemp("lm") / "w5.arpa"
+    lm_cases.write_lm(str(p), order=5, seed=1)
+    return str(p)
+
+
+def f32(x):
+    return np.float32(x)
+
+
+def test_backoff_scoring_by_hand(hand):
+    m = olm.ArpaModel(hand)
+    assert m.order == 3 and "a" in m and "zz" not in m
+    s, st = m.base_score(m.begin_state(), "a")            # bigram <s> a
+    assert s == f32(-0.4) and st == ("<s>", "a")
+    s, st = m.base_score(st, "b")                          # trigram <s> a b
+    assert s == f32(-0.1) and st == ("a", "b")
+    s, st2 = m.base_score(st, "a")                         # (a b a) missing -> bigram b a + backoff(a b)
+    assert s == f32(f32(-0.3) + f32(-0.125))
+    s, _ = m.base_score(st, "c")                           # only the unigram: + backoff(b) + backoff(a b), shorter first
+    assert s == f32(f32(f32(-0.9) + f32(-0.2)) + f32(-0.125))
+    s, st3 = m.base_score(st, "zz")                        # out of vocabulary -> <unk>
+    assert s == f32(f32(f32(-1.0) + f32(-0.2)) + f32(-0.125)) and st3 == ("b", "<unk>")
+    s, _ = m.base_score(st3, "a")                          # nothing continues <unk>; its back-off is 0
+    assert s == f32(-0.6)
+
+
+def test_language_model_formulas(hand):
+    L = olm.LanguageModel(olm.ArpaModel(hand), alpha=0.6, beta=0.25)
+    s, st = L.score(L.start_state(), "a")
+    assert s == pytest.approx(0.6 * float(f32(-0.4)) * math.log(10) + 0.25, abs=1e-12)
+    s, _ = L.score(st, "zz")
+    assert s == pytest.approx(0.6 * (float(f32(f32(-1.0) + f32(-0.3)) + f32(-0.25)) - 10.0) * math.log(10) + 0.25, abs=1e-6)
+    s, _ = L.score(st, "b", is_last_word=True)             # + log10 p(</s> | a b)
+    assert s == pytest.approx(0.6 * (float(f32(-0.1)) + float(f32(-0.05))) * math.log(10) + 0.25, abs=1e-9)
+    assert L.score_partial_token("a") == 0.0
+    assert L.score_partial_token("q") == -10.0
+    assert L.score_partial_token("qqqqqqqq") == pytest.approx(-10.0 * 8 / 6)
+
+
+def test_tables_reproduce_the_file(arpa5):
+    """Every n-gram of the file is reachable through the forward-trie hash table, with its fp32 values; the character
+    trie answers prefix / word queries like a set of the unigrams."""
+    t = plm.build_tables(arpa5, LABEL_TEXT, 0.5, 1.0)
+    order, tables = plm.parse_arpa(arpa5)
+    assert t.order == order == 5
+    wid = {w: i for i, w in enumerate(t.words)}
+    mask = np.uint64(len(t.ngram_keys) - 1)
+
+    def child(parent, w):
+        key = np.uint64(((parent + 1) << 32) | w)
+        s = plm.lm_hash(np.asarray([key]))[0] & mask
+        while True:
+            if t.ngram_keys[s] == key:
+                return int(t.ngram_vals[s])
+            if t.ngram_keys[s] == 0:
+                return -1
+            s = (s + np.uint64(1)) & mask
+
+    n_checked = 0
+    for n in range(1, order + 1):
+        for gram, (p, b) in tables[n - 1].items():
+            i = wid[gram[0]]
+            for w in gram[1:]:
+                i = child(i, wid[w])
+                assert i >= 0, gram
+            assert t.ngram_prob[i] == np.float32(p) and t.ngram_backoff[i] == np.float32(b)
+            n_checked += 1
+    assert n_checked == len(t.ngram_prob)
+    assert child(wid["the"], wid["<s>"]) == -1
+    lab = {c: k for k, c in enumerate(LABEL_TEXT) if k}
+    prefixes = {w[:k] for w in t.words for k in range(1, len(w) + 1) if all(c in lab for c in w[:k])}
+    for probe in sorted(prefixes) + ["q", "thx", "catsx", "understandingly"]:
+        node = 0
+        for c in probe:
+            node = t.trie_child[node, lab[c]] if node >= 0 else -1
+        assert (node >= 0) == (probe in prefixes), probe
+        if node >= 0:
+            assert (t.trie_word[node] >= 0) == (probe in wid), probe
+            if probe in wid:
+                assert t.trie_word[node] == wid[probe]
+    assert t.bos == wid["<s>"] and t.eos == wid["</s>"] and t.unk == wid["<unk>"]
+
+
+def test_hash_matches_the_library(lib):
+    keys = np.asarray([1, 2**32 + 7, 2**63 + 12345, 2**64 - 1], dtype=np.uint64)
+    assert [int(lib.ssd_lm_hash(int(k))) for k in keys] == [int(h) for h in plm.lm_hash(keys)]
+
+
+def _texts(ids):
+    return ["".join(ob.UNK_GLYPH if i == V.unk_id else V.tokens[i] for i in s) for s in ids]
+
+
+def _check(lib, path, lp, ln, width, prune, bias, alpha, beta, tol=2e-5):
+    L = olm.LanguageModel(olm.ArpaModel(path), alpha=alpha, beta=beta)
+    want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, blank_bias=bias, lm=L).decode_with_lm_scores(lp, ln)
+    tab = plm.build_tables(path, LABEL_TEXT, alpha, beta)
+    (ids, score), = harness.beam_lm(lib, lp, ln, V.blank_id, V.pad_id, SPACE, tab, [(width, prune, bias, -5.0)])
+    assert _texts(ids) == [w[0] for w in want]
+    assert np.abs(score - np.asarray([w[2] for w in want])).max() <= tol
+    return want
+
+
+@pytest.mark.parametrize("order,width,prune,bias,alpha,beta,boost,seed", [
+    (3, 20, -10.0, 0.0, 0.6, 0.3, 3.0, 1),
+    (5, 30, -12.0, 0.1, 0.9, 1.5, 3.5, 2),
+    (5, 8, -10.0, 0.0, 0.6, 0.0, 6.0, 3),     # confident input: the in-place frame updates run
+    (3, 1, -10.0, 0.0, 0.6, 0.0, 3.0, 4),
+])
+def test_lm_kernel_matches_oracle(lib, arpa3, arpa5, order, width, prune, bias, alpha, beta, boost, seed):
+    path = arpa3 if order == 3 else arpa5
+    lp, ln = lm_cases.spelled_log_probs(lm_cases.SENTENCES, 84, seed=seed, boost=boost)
+    ln = [84, 80, 84, 71, 84, 60, 84, 84]
+    want = _check(lib, path, lp, ln, width, prune, bias, alpha, beta)
+    if width >= 20:  # the LM does its job on this input: mostly dictionary words come out
+        words = [w for t, _, _ in want for w in t.split()]
+        assert sum(w in lm_cases.WORDS for w in words) >= 0.7 * len(words)
+
+
+def test_lm_changes_the_transcript(lib, arpa3):
+    lp, ln = lm_cases.spelled_log_probs(lm_cases.SENTENCES[:3], 84, seed=1)
+    no_lm = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 20, -10.0)(lp, ln)
+    with_lm = [w[0] for w in _check(lib, arpa3, lp, ln, 20, -10.0, 0.0, 0.6, 0.3)]
+    assert no_lm != with_lm
+
+
+def test_zero_weight_lm_equals_the_no_lm_search(lib, tmp_path):
+    """An order-2 model with alpha = beta = unk offset = 0 ranks by the acoustic score alone and keys its history on one
+    word: the LM kernel (every beam proposes every label) must then reproduce the no-LM kernel (staircase rows)."""
+    path = str(tmp_path / "w2.arpa")
+    lm_cases.write_lm(path, order=2, seed=3)
+    tab = plm.build_tables(path, LABEL_TEXT, 0.0, 0.0, unk_score_offset=0.0)
+    from silent_speech_decoder_b200 import synth
+
+    lp = np.concatenate([synth.flat(2, 50, 5).numpy(), synth.peaked(2, 50, 6).numpy()])
+    ln = [50, 41, 50, 33]
+    for width in (12, 40):
+        (ids, score), = harness.beam_lm(lib, lp, ln, V.blank_id, V.pad_id, SPACE, tab, [(width, -10.0, 0.0, -5.0)])
+        ids0, score0 = harness.beam(lib, lp, ln, V.blank_id, V.pad_id, SPACE, width, -10.0, 0.0, -5.0)
+        assert ids == ids0
+        np.testing.assert_allclose(score, score0, rtol=0, atol=1e-9)
+
+
+def test_end_of_sentence_term_and_the_score_cache(lib, hand):
+    """Upstream's quirk, restated: the last word gets log10 p(</s> | ..) only if its closed text was never scored
+    before.  'a' then blank: scored with </s>.  'a' then a frame where space is a candidate: 'a' entered the cache as a
+    closed text in that frame, the final pass finds it there and adds no </s> term."""
+    a, sp = V.tokens.index("a"), V.tokens.index(" ")
+    lp = np.full((2, 3, V.size), -30.0, dtype=np.float32)
+    lp[:, 0, a] = 0.0
+    lp[:, 1, V.blank_id] = 0.0
+    lp[0, 2, V.blank_id] = 0.0
+    lp[1, 2, V.blank_id] = math.log(0.6)
+    lp[1, 2, sp] = math.log(0.4)
+    want = _check(lib, hand, lp, [3, 3], 10, -10.0, 0.0, 0.7, 0.1)
+    assert [w[0] for w in want] == ["a", "a"]
+    m = olm.ArpaModel(hand)
+    k = 0.7 * math.log(10)
+    # p(a | <s>), and p(</s> | <s> a) = bigram (a </s>) + back-off of (<s> a)
+    with_eos = k * (float(f32(-0.4)) + float(f32(f32(-0.6) + f32(-0.25)))) + 0.1
+    without = k * float(f32(-0.4)) + 0.1
+    assert want[0][2] - want[0][1] == pytest.approx(with_eos, abs=1e-9)
+    assert want[1][2] - want[1][1] == pytest.approx(without, abs=1e-9)
+    assert m.order == 3
+
+
+def test_lm_entry_validates_its_tables(lib, arpa3):
+    tab = plm.build_tables(arpa3, LABEL_TEXT, 0.5, 0.5)
+    lp = np.zeros((1, 4, V.size), dtype=np.float32)
+    bad = plm.build_tables(arpa3, LABEL_TEXT[:-1], 0.5, 0.5)  # trie laid out for the wrong number of labels
+    with pytest.raises(ValueError):
+        harness.beam_lm(lib, lp, [4], V.blank_id, V.pad_id, SPACE, bad, [(5, -10.0, 0.0, -5.0)])
+    tab.order = 9
+    with pytest.raises(Exception):
+        harness.beam_lm(lib, lp, [4], V.blank_id, V.pad_id, SPACE, tab, [(5, -10.0, 0.0, -5.0)])
+
+
+def test_build_decoder_refuses_a_binary_lm():
+    with pytest.raises(ValueError):
+        ctc.build_decoder("beam", V, lm_path="model.bin")
