@@ -248,6 +248,66 @@ def cpu_beam_reference(n_utts: int, kind: str, budget_s: float = 25.0, T: int = 
     return n / dt, cores, n, one
 
 
+LM_CFG = {"words": 2000, "lines": 20000, "order": 5, "alpha": 0.6, "beta": 0.0, "seed": 4242}
+
+
+def lm_workload(n: int, T: int, seed: int):
+    """Scope row f-4 at config 3's shape: a 5-gram word LM (what build_char_lm.py:35-40 asks lmplz for) over a synthetic
+    2000-word domain, and n utterances whose posteriors spell in-domain sentences with a rival letter on every emitting
+    frame (no-LM beam search gets most words wrong on them; the LM decides).  -> (lp, lengths, arpa path)"""
+    import tempfile
+
+    from silent_speech_decoder_b200 import synth
+    from silent_speech_decoder_b200.data.vocab import Vocab
+
+    c = LM_CFG
+    words = synth.word_list(c["words"], c["seed"])
+    arpa = os.path.join(tempfile.gettempdir(), f"ssd_bench_lm_{os.getpid()}.arpa")
+    synth.write_arpa(arpa, synth.word_corpus(words, c["lines"], c["seed"] + 1), c["order"])
+    sents = synth.word_corpus(words, n, seed + 17)
+    lp, ln = synth.spelled(sents, Vocab.default().token_to_id, T, seed)
+    return lp, ln, arpa
+
+
+_LM_DEC = None
+
+
+def _beam_lm_init(arpa, width, prune, alpha, beta):
+    global _LM_DEC
+    from oracle import beam as ob
+    from oracle import lm as olm
+    from silent_speech_decoder_b200.data.vocab import Vocab
+
+    v = Vocab.default()
+    _LM_DEC = ob.BeamDecoder(v.tokens, v.blank_id, v.pad_id, width, prune, lm=olm.LanguageModel(olm.ArpaModel(arpa), alpha, beta))
+
+
+def _beam_lm_worker(job):
+    lp, n = job
+    return _LM_DEC(lp[None], [n])[0]
+
+
+def cpu_beam_lm_reference(n_utts: int, budget_s: float = 12.0, T: int = CFG3["T"], width: int = CFG3["width"], seed: int = CFG3["seed"]):
+    """oracle/beam.py + oracle/lm.py (restatements of pyctcdecode / kenlm; both unavailable) over all host cores."""
+    import multiprocessing as mp
+
+    lp, ln, arpa = lm_workload(n_utts, T, seed)
+    jobs = [(lp[i].numpy(), int(ln[i])) for i in range(n_utts)]
+    cores = os.cpu_count() or 1
+    c = LM_CFG
+    _beam_lm_init(arpa, width, CFG3["prune"], c["alpha"], c["beta"])
+    t0 = time.perf_counter()
+    _beam_lm_worker(jobs[0])
+    one = time.perf_counter() - t0
+    n = min(n_utts, max(cores, int(budget_s * cores / max(one, 1e-3))))
+    with mp.get_context("fork").Pool(cores) as pool:  # forked workers inherit the decoder built above
+        t0 = time.perf_counter()
+        pool.map(_beam_lm_worker, jobs[:n], chunksize=1)
+        dt = time.perf_counter() - t0
+    os.unlink(arpa)
+    return n / dt, cores, n, one
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -511,6 +571,76 @@ def bench_decode(args, rank, world, dev, method: str, kind: str, n: int, T: int,
     return out
 
 
+def bench_beam_lm(args, rank, world, dev, n: int, T: int, width: int, seed: int):
+    """Row f-4: LM-fused beam search (ssd_ctc_beam_lm) on config 3's shape."""
+    from silent_speech_decoder_b200 import ops
+    from silent_speech_decoder_b200.data.vocab import Vocab
+    from silent_speech_decoder_b200.decoding import ctc
+    from silent_speech_decoder_b200.decoding import lm as plm
+
+    v = Vocab.default()
+    c = LM_CFG
+    lp, ln, arpa = lm_workload(n, T, seed + rank)
+    text, space = ctc._beam_label_strings(v)
+    keep = [i for i in range(v.size) if i not in {v.blank_id, v.pad_id}]
+    tables = plm.build_tables(arpa, [""] + [text[i] for i in keep], c["alpha"], c["beta"])
+    x, ln_d = lp.to(dev), ln.to(dev)
+    settings = [(width, CFG3["prune"], 0.0, -5.0)]
+
+    def kernel():
+        return ops.beam_lm_ids(x, ln_d, v.blank_id, v.pad_id, space, tables, settings)
+
+    for _ in range(2):
+        kernel()
+    barrier(world)
+    steps = 3
+    l0 = ops.LAUNCHES["beam"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tok, cnt, _ = kernel()
+    e1.record()
+    barrier(world)
+    ms = dist_max(e0.elapsed_time(e1), world, dev) / steps
+    launches = ops.LAUNCHES["beam"] - l0
+    hyp = ctc._rows_to_strings(tok[0], cnt[0], text, normalise_space=True)
+    no_lm = ctc.build_decoder("beam", v, beam_width=width, beam_prune_logp=CFG3["prune"])(x[:512], ln_d[:512])
+    from silent_speech_decoder_b200 import synth
+
+    sents = synth.word_corpus(synth.word_list(c["words"], c["seed"]), n, seed + rank + 17)  # the sentences lm_workload spelled
+    cut = [s[: max(1, (T - 2) // 2)] for s in sents]
+    exact = sum(h == " ".join(r.split()) for h, r in zip(hyp, cut)) / len(hyp)
+    exact0 = sum(h == " ".join(r.split()) for h, r in zip(no_lm, cut[:512])) / len(no_lm)
+    peak, peak_src = measured_peak_gbs()
+    achieved = DECODE_BYTES_PER_FRAME * n * T / (ms * 1e-3) / 1e9
+    out = {
+        "metric": f"ctc_beam{width}_lm_decode_utterances_per_sec", "value": world * n / (ms * 1e-3), "unit": "utterances/s",
+        "ms_per_step": ms, "dtype": "f64",
+        "config": {"workload": f"row f-4 at cfg3's shape: LM-fused beam decode of {n} utterances per GPU, T={T}, V=48, width {width}, prune -10, "
+                               f"{c['order']}-gram word LM over {c['words']} words ({len(tables.ngram_prob)} n-grams), alpha {c['alpha']}, beta {c['beta']}",
+                   "l2": f"input {n * T * 48 * 4 / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world} by utterance, no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "ssd::beam_kernel<true>", "kernel_ms": ms,
+                     "algorithmic_bytes": DECODE_BYTES_PER_FRAME * n * T,
+                     "note": "latency/issue bound like the no-LM search; every beam proposes every candidate label (no staircase bound under LM scores)"},
+        "gpu_launches": launches,
+        "sentences_exactly_right": {"with_lm": exact, "without_lm_first_512": exact0},
+    }
+    decoder = ctc.build_decoder("beam", v, lm_path=arpa, beam_width=width, alpha=c["alpha"], beta=c["beta"], beam_prune_logp=CFG3["prune"])
+    h_lp, h_ln = lp.pin_memory(), ln.pin_memory()
+    del x
+    decoder(h_lp, h_ln)
+    barrier(world)
+    t0 = time.perf_counter()
+    texts = decoder(h_lp, h_ln)
+    e2e_ms = dist_max(1e3 * (time.perf_counter() - t0), world, dev)
+    out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "utterances/s", "h2d_bytes_per_step": h_lp.numel() * 4 + h_ln.numel() * 8,
+                  "d2h_bytes_per_step": n * 4 + sum(len(t) for t in texts) * 4, "ms_per_step": e2e_ms,
+                  "api": "build_decoder('beam', vocab, lm_path=<arpa>, alpha, beta)(log_probs, lengths) on pinned host tensors"}
+    os.unlink(arpa)
+    return out
+
+
 def bench_cfg4(args, rank, world, dev):
     """Config 4: beam width sweep 1/10/50/200 on long utterances (T=4000), peaked and flat, 256 utterances per GPU."""
     c = CFG4
@@ -642,6 +772,7 @@ def run_native(args, rank, world, local):
                 secondary[f"beam50_{kind}"] = {k: r[k] for k in keep if k in r}
             r = bench_decode(args, rank, world, dev, "greedy", "flat", CFG3["N"], CFG3["T"], 0, CFG3["seed"])
             secondary["greedy"] = {k: r[k] for k in keep if k in r}
+            secondary["beam50_lm"] = bench_beam_lm(args, rank, world, dev, CFG3["N"], CFG3["T"], CFG3["width"], CFG3["seed"])
             secondary["cfg4_width_sweep"] = bench_cfg4(args, rank, world, dev)
             secondary["cfg5_eval"] = bench_cfg5(args, rank, world, dev)
         time.sleep(0.12)
@@ -658,6 +789,11 @@ def run_native(args, rank, world, local):
                         "value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
                         "sample": f"{n} cfg3 utterances ({kind}) over {cores} processes; oracle/beam.py restatement of pyctcdecode (library unavailable)",
                         "single_process_utt_per_s": 1.0 / one}
+                v, cores, n, one = cpu_beam_lm_reference(128, budget_s=10.0)
+                secondary["beam50_lm"]["cpu_baseline"] = {
+                    "value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
+                    "sample": f"{n} utterances of the same workload over {cores} processes; oracle/beam.py + oracle/lm.py restatements of "
+                              "pyctcdecode / kenlm (both unavailable)", "single_process_utt_per_s": 1.0 / one}
         elif args.workload == "beam":
             v, cores, n, one = cpu_beam_reference(min(args.utts, 256), args.beam_input, T=args.T, width=args.width)
             line["cpu_baseline"] = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",

@@ -172,3 +172,112 @@ def peaked_aligned(
     lp = torch.log_softmax(noise, dim=-1)
     out = (lp, torch.from_numpy(tg), torch.from_numpy(tl))
     return out + (a,) if return_alignment else out
+
+
+# ------------------------------------------------------------------ language-model fusion inputs (scope row f-4)
+def word_list(n_words: int, seed: int):
+    """``n_words`` distinct lower-case "words" (2-9 letters, English letter frequencies)."""
+    import numpy as np
+
+    rng = np.random.default_rng(int(seed))
+    letters = [c for c in _ENGLISH if c.isalpha()]
+    p = np.asarray([_ENGLISH[c] for c in letters])
+    p = p / p.sum()
+    out, seen = [], set()
+    while len(out) < n_words:
+        w = "".join(rng.choice(letters, size=int(rng.integers(2, 10)), p=p))
+        if w not in seen:
+            seen.add(w)
+            out.append(w)
+    return out
+
+
+def word_corpus(words, n_lines: int, seed: int, lo: int = 3, hi: int = 12):
+    """Sentences over ``words``: Zipf-distributed unigrams with a sparse first-order chain, so that higher n-gram
+    orders carry information (what transcripts of a small domain look like to ``lmplz``)."""
+    import numpy as np
+
+    rng = np.random.default_rng(int(seed))
+    n = len(words)
+    zipf = 1.0 / np.arange(1, n + 1)
+    zipf /= zipf.sum()
+    follow = rng.integers(0, n, size=(n, 4))
+    lines = []
+    for _ in range(n_lines):
+        k = int(rng.choice(n, p=zipf))
+        line = [words[k]]
+        for _ in range(int(rng.integers(lo, hi + 1)) - 1):
+            k = int(follow[k, int(rng.integers(4))]) if rng.random() < 0.75 else int(rng.choice(n, p=zipf))
+            line.append(words[k])
+        lines.append(" ".join(line))
+    return lines
+
+
+def write_arpa(path, corpus, order: int = 5, discount: float = 0.5) -> None:
+    """A well-formed ARPA file from n-gram counts of ``corpus`` (absolute discounting; every prefix and suffix of a
+    listed n-gram is listed, as in ``lmplz`` output -- ``lmplz`` itself, which the reference shells out to at
+    ``build_char_lm.py:35-40``, is not in this image).  The probabilities are plausible, not a tuned model."""
+    import math
+
+    counts = [dict() for _ in range(order)]
+    for line in corpus:
+        w = ["<s>"] + line.split() + ["</s>"]
+        for n in range(1, order + 1):
+            for i in range(len(w) - n + 1):
+                g = tuple(w[i: i + n])
+                counts[n - 1][g] = counts[n - 1].get(g, 0) + 1
+    counts[0].setdefault(("<unk>",), 0)
+    total = sum(c for g, c in counts[0].items() if g != ("<s>",)) + 1.0
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\\data\\\n")
+        for n in range(order):
+            f.write(f"ngram {n + 1}={len(counts[n])}\n")
+        for n in range(order):
+            f.write(f"\n\\{n + 1}-grams:\n")
+            longer = {}
+            if n + 1 < order:
+                for h in counts[n + 1]:
+                    longer[h[:-1]] = longer.get(h[:-1], 0) + 1
+            for g in sorted(counts[n]):
+                c = counts[n][g]
+                denom = total if n == 0 else counts[n - 1][g[:-1]]
+                logp = -99.0 if g == ("<s>",) else math.log10(max(c - discount, 0.1) / denom)
+                if n + 1 < order:
+                    types = longer.get(g, 0)
+                    bo = math.log10(min(1.0, discount * types / max(c, 1)) + 1e-3) if types else 0.0
+                    f.write(f"{logp:.6f}\t{' '.join(g)}\t{bo:.6f}\n")
+                else:
+                    f.write(f"{logp:.6f}\t{' '.join(g)}\n")
+        f.write("\n\\end\\\n")
+
+
+def spelled(sentences, token_to_id, T: int, seed: int, V: int = V_DEFAULT, blank: int = BLANK_DEFAULT, boost: float = 5.0,
+            rival: float = 2.5):
+    """(log_probs (B,T,V) fp32, lengths (B,) int64): posteriors laid on a random CTC alignment of each sentence's
+    characters, with a random rival letter boosted on every emitting frame so that several spellings compete and an LM
+    has something to decide.  Sentences are cut to what fits T frames."""
+    import numpy as np
+
+    rng = np.random.default_rng(int(seed))
+    B = len(sentences)
+    x = torch.randn(B, T, V, generator=_gen(seed), dtype=torch.float32).numpy()
+    letter_ids = np.asarray([i for t, i in token_to_id.items() if len(t) == 1 and t.isalpha()])
+    for b, s in enumerate(sentences):
+        ids = np.asarray([token_to_id[c] for c in s if c in token_to_id][: max(1, (T - 2) // 2)], dtype=np.int64)
+        n = len(ids)
+        need_blank = np.concatenate(([False], ids[1:] == ids[:-1]))
+        opt = (~need_blank) & (np.arange(n) > 0) & (rng.random(n) < 0.5)
+        room = T - n - int(need_blank.sum())
+        if int(opt.sum()) > room:
+            idx = np.flatnonzero(opt)
+            opt[idx[room:]] = False
+        with_blank = need_blank | opt
+        ext = np.full(n + int(with_blank.sum()), blank, dtype=np.int64)
+        ext[np.arange(n) + np.cumsum(with_blank)] = ids
+        reps = np.bincount(rng.integers(0, ext.shape[0], size=T - ext.shape[0]), minlength=ext.shape[0]) + 1
+        path = np.repeat(ext, reps)[:T]
+        x[b, np.arange(T), path] += boost
+        emit = np.flatnonzero(path != blank)
+        x[b, emit, letter_ids[rng.integers(0, len(letter_ids), size=len(emit))]] += rival
+    lp = torch.log_softmax(torch.from_numpy(x), dim=-1)
+    return lp, torch.full((B,), T, dtype=torch.int64)

@@ -247,3 +247,22 @@ def test_lm_entry_validates_its_tables(lib, arpa3):
 def test_build_decoder_refuses_a_binary_lm():
     with pytest.raises(ValueError):
         ctc.build_decoder("beam", V, lm_path="model.bin")
+
+
+def test_lm_restatement_matches_upstream(golden_dir, tmp_path):
+    """Consumes the LM cases of tests/golden/beam_upstream.npz (REAL pyctcdecode + kenlm, written by
+    oracle/make_beam_golden_upstream.py where both are installed).  Absent here: LM parity UNPINNED."""
+    path = os.path.join(golden_dir, "beam_upstream.npz")
+    if not os.path.exists(path) or "lm5_w50.text" not in np.load(path).files:
+        pytest.skip("no upstream LM cases in tests/golden/beam_upstream.npz (needs pyctcdecode + kenlm): LM parity unpinned")
+    from oracle.make_beam_golden_upstream import LM_CASES, lm_case_inputs
+
+    z = np.load(path)
+    for name, order, words, B, T, seed, width, prune, bias, alpha, beta in LM_CASES:
+        arpa = str(tmp_path / f"{name}.arpa")
+        lp, ln = lm_case_inputs(order, words, B, T, seed, arpa)
+        L = olm.LanguageModel(olm.ArpaModel(arpa), alpha=alpha, beta=beta)
+        out = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, blank_bias=bias, lm=L).decode_with_lm_scores(lp, ln)
+        assert [o[0] for o in out] == list(z[f"{name}.text"]), name
+        np.testing.assert_allclose([o[1] for o in out], z[f"{name}.logit_score"], rtol=0, atol=1e-4, err_msg=name)
+        np.testing.assert_allclose([o[2] for o in out], z[f"{name}.lm_score"], rtol=0, atol=1e-4, err_msg=name)
