@@ -18,4 +18,8 @@ Pinning status:
   (no network).  ``beam.py`` restates its published algorithm from memory and
   follows the reference's own call site ``src/decoding/ctc.py:47-99`` for the
   wrapper.  The reference holds no test or golden vector for beam search.
+* ``lm``        -- PARITY UNPINNED: ``kenlm`` back-off scoring and pyctcdecode's ``LanguageModel`` /
+  ``_get_lm_beams`` restated from memory (scope row f-4); checked only against hand-computed
+  answers on a three-gram file.  ``make_beam_golden_upstream.py`` writes upstream LM fixtures
+  where both libraries exist.
 """

@@ -36,6 +36,7 @@
 // End: merge blank-/char-ending and trailing-space variants, arg-max, walk back-pointers.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ssd_common.cuh"
 
@@ -49,6 +50,10 @@ namespace ssd {
 #endif
 #ifndef SSD_BEAM_MINCTAS
 #define SSD_BEAM_MINCTAS 8
+#endif
+#ifndef SSD_BEAM_ROWDIV
+#define SSD_BEAM_ROWDIV 0  // no-LM kernel, uniform proposal rows: row = index / width instead of the binary search over row offsets
+                           // (measured on config 3: 184.1 k against 187.1 k utterances/s confident, flat equal; the LM kernel always divides)
 #endif
 #ifndef SSD_BEAM_CONS
 #define SSD_BEAM_CONS 64
@@ -112,9 +117,10 @@ __host__ __device__ inline int beam_table_slots(int W) {
 }
 
 // barrier among the consumer threads: a warp barrier when there is a single consumer warp
+template <int CONS>
 __device__ __forceinline__ void cons_sync() {
-  if (BM_CONS == 32) __syncwarp();
-  else bar_sync(BAR_CONS, BM_CONS);
+  if (CONS == 32) __syncwarp();
+  else bar_sync(BAR_CONS, CONS);
 }
 
 // ------------------------------------------------------------------ small device helpers
@@ -228,8 +234,9 @@ __host__ __device__ inline int beam_hk_slots(int W, int NCAND) {
 
 // scratch shared by the bucket cut (bucket of each alive entry, boundary list: 2 x NCAND ints) and, after it, the
 // history-key table (key, best score, lowest index: 20 bytes per slot)
-__host__ __device__ inline size_t beam_scratch_bytes(int W, int NCAND) {
-  const size_t a = 8 * (size_t)NCAND, b = 20 * (size_t)beam_hk_slots(W, NCAND);
+__host__ __device__ inline size_t beam_scratch_bytes(int W, int NCAND, bool lm = false) {
+  // (the LM kernel, whose candidate capacity is 5-10 times larger, keeps the two lists as 16-bit values)
+  const size_t a = (lm ? 4 : 8) * (size_t)NCAND, b = 20 * (size_t)beam_hk_slots(W, NCAND);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -245,14 +252,15 @@ __host__ __device__ inline size_t lm_gen_bytes(int W, int order) {
 __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, int NCAND, int lm_order = 0) {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t s = 0;
-  if (lm_order > 0) s += 2 * lm_gen_bytes(W, lm_order) + al(8 * (size_t)NCAND);  // LM state x2, ranking scores
+  if (lm_order > 0) s += 2 * lm_gen_bytes(W, lm_order);  // LM state of the prefixes, two generations
   s += 2 * prefix_gen_bytes(W);                              // prefix tables, two generations
   s += 3 * al(8 * (size_t)W);                               // tot, newb, newnb
   s += 5 * al(4 * (size_t)W);                               // par, rank2p, rowoff, keepflags, slot
   s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
-  s += al(8 * (size_t)NCAND) + al(4 * (size_t)NCAND);       // candidate score, desc
+  s += al(8 * (size_t)NCAND);                               // candidate score (LM: the ranking score)
+  if (lm_order == 0) s += al(4 * (size_t)NCAND);            // candidate desc (LM: rows are uniform, desc = f(index))
   s += al(4 * (size_t)NCAND);                               // alive idx
-  s += beam_scratch_bytes(W, NCAND) + al(4 * 256);          // bucket cut scratch / history-key table, histogram
+  s += beam_scratch_bytes(W, NCAND, lm_order > 0) + al(4 * 256);  // bucket cut scratch / history-key table, histogram
   s += al(4 * (size_t)(W + 1));                             // the W survivors of the bucket cut
   s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
   s += al(8 * (size_t)(W + 1));                             // sel_hk
@@ -505,8 +513,19 @@ __device__ inline bool seen_find(unsigned long long* tab, unsigned long long mas
 // ------------------------------------------------------------------ the kernel
 // LM = false: the no-LM search (the reference's configured path).  LM = true: the same search ranked by acoustic +
 // LM score; every `if constexpr (LM)` block below is absent from the no-LM instantiation.
+#ifndef SSD_BEAM_LM_MINCTAS
+#define SSD_BEAM_LM_MINCTAS 3
+#endif
+#ifndef SSD_BEAM_LM_CONS
+#define SSD_BEAM_LM_CONS 64  // consumer threads of the LM kernel (a frame has 5-10 times the candidates of a no-LM one)
+#endif
+constexpr int BM_LM_CONS = SSD_BEAM_LM_CONS;
+constexpr int BM_LM_THREADS = BM_LM_CONS + 32;
+static_assert(BM_LM_CONS % 32 == 0 && BM_LM_CONS <= 128 && BM_CONS <= 128, "per-warp scratch in Scal holds four consumer warps");
 template <bool LM>
-__global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
+__global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM_LM_MINCTAS : SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
+  constexpr int CONS = LM ? BM_LM_CONS : BM_CONS;  // consumer threads; one more warp produces
+  constexpr int THREADS = CONS + 32;
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
   const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
@@ -527,11 +546,12 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
   int* oslot = (int*)carve(sp, 4 * WC);
   unsigned long long* tkeys = (unsigned long long*)carve(sp, 8 * TS);
   int* tvals = (int*)carve(sp, 4 * TS);
-  double* cscore = (double*)carve(sp, 8 * NCAND);
-  uint32_t* cdesc = (uint32_t*)carve(sp, 4 * NCAND);
+  double* cscore = (double*)carve(sp, 8 * NCAND);  // LM: the RANKING score (acoustic + LM); the acoustic one is recomputed for survivors
+  uint32_t* cdesc = LM ? nullptr : (uint32_t*)carve(sp, 4 * NCAND);
   int* aidx = (int*)carve(sp, 4 * NCAND);
-  int* abkt = (int*)carve(sp, beam_scratch_bytes(WC, NCAND));  // after the cut this scratch holds the history-key table
-  int* blist = abkt + NCAND;
+  using bk_t = typename std::conditional<LM, short, int>::type;
+  bk_t* abkt = (bk_t*)carve(sp, beam_scratch_bytes(WC, NCAND, LM));  // after the cut this scratch holds the history-key table
+  bk_t* blist = abkt + NCAND;
   int* hist = (int*)carve(sp, 4 * 256);
   int* bidx = (int*)carve(sp, 4 * (WC + 1));
   int* sel = (int*)carve(sp, 4 * (WC + 1));
@@ -580,15 +600,15 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
     sp = lp0 + 2 * gb;
     lm_gs8 = (int)(gb / 8);
     lm_gs4 = (int)(gb / 4);
-    cfused = (double*)carve(sp, 8 * NCAND);
+    cfused = cscore;
   }
-  const double* const rscore = LM ? cfused : cscore;  // what ranks and prunes a candidate
+  const double* const rscore = cscore;  // what ranks and prunes a candidate
   unsigned long long* const seen = LM ? P.seen + (int64_t)blockIdx.x * P.seen_cap : nullptr;
   (void)CX; (void)lm_gs4;
 
   const int tid = (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp == BM_CONS / 32;
+  const bool producer = warp == CONS / 32;
   const int tmask = TS - 1;
   uint2* nodes = P.nodes + (int64_t)blockIdx.x * P.node_cap;
   const int space_lbl_vocab = P.space;
@@ -659,10 +679,10 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       unsigned long long slots = 1024ull;
       while (slots < 2ull * (unsigned long long)len * (unsigned long long)W && (int64_t)slots < P.seen_cap) slots <<= 1;
       seen_mask = slots - 1ull;
-      for (unsigned long long i = (unsigned long long)tid; i < slots; i += BM_THREADS) seen[i] = 0ull;
+      for (unsigned long long i = (unsigned long long)tid; i < slots; i += THREADS) seen[i] = 0ull;
     }
-    for (int i = tid; i < TS; i += BM_THREADS) tkeys[i] = 0ull;
-    for (int i = tid; i < HKS; i += BM_THREADS) {
+    for (int i = tid; i < TS; i += THREADS) tkeys[i] = 0ull;
+    for (int i = tid; i < HKS; i += THREADS) {
       hk_keys[i] = 0ull;
       hk_best[i] = 0ull;
       hk_idx[i] = 0x7fffffff;
@@ -730,7 +750,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         const long long pf_t1 = clock64();
         pf_prod += pf_t1 - pf_t0;
 #endif
-        bar_sync(BAR_FRAME, BM_THREADS);
+        bar_sync(BAR_FRAME, THREADS);
 #ifdef SSD_BEAM_PROF
         pf_wait += clock64() - pf_t1;
         if (t == len - 1 && blockIdx.x == 0 && lane == 0)
@@ -790,7 +810,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         const double rb = (double)F.rl[c1];
         double m = neg_inf();
         bool general = false;
-        for (int p = tid; p < np; p += BM_CONS) {
+        for (int p = tid; p < np; p += CONS) {
           double v;
           uint32_t lc;
           if (blank_only) {
@@ -809,11 +829,11 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         m = warp_max_d(m);
         if (lane == 0) sc->wmax[warp] = m;
         if (tid == 0) sc->n_b = 0;
-        cons_sync();
+        cons_sync<CONS>();
         double mm = sc->wmax[0];
-        for (int w = 1; w < BM_CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
+        for (int w = 1; w < CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
         const double cut = mm + (double)s_prune;
-        for (int p = tid; p < np; p += BM_CONS) {
+        for (int p = tid; p < np; p += CONS) {
           double v = newb[p];
           if constexpr (LM) v += lm_of(p);
           if (!(v >= cut) || v == -INFINITY) general = true;
@@ -822,9 +842,9 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
             if (q != p && sel_hk[q] == hk) general = true;
         }
         if (general) sc->n_b = 1;
-        cons_sync();
+        cons_sync<CONS>();
         if (sc->n_b == 0) {
-          for (int p = tid; p < np; p += BM_CONS) {
+          for (int p = tid; p < np; p += CONS) {
             if (blank_only) {
               A.sb[p] = newb[p];
               A.snb[p] = neg_inf();
@@ -837,7 +857,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           pf_fast += pf_t1 - pf_t0;
           ++pf_nfast;
 #endif
-          bar_sync(BAR_FRAME, BM_THREADS);  // same generation, same table; frame t+1's record is visible
+          bar_sync(BAR_FRAME, THREADS);  // same generation, same table; frame t+1's record is visible
 #ifdef SSD_BEAM_PROF
           pf_wait += clock64() - pf_t1;
 #endif
@@ -851,18 +871,18 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       // ---- phase 1: tot, parent slot.  (When no staircase row is cut -- see phase 2 -- nobody needs another prefix's
       // tot before phase 3 except for the parent's, which is then recomputed on the spot: phases 1 and 2 share a barrier.)
       const bool cut_rows = !LM && nc1 > W / np + 1;  // under LM scores the staircase bound does not hold: full rows
-      for (int p = tid; p < np; p += BM_CONS) {
+      for (int p = tid; p < np; p += CONS) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
         par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
       }
-      if (cut_rows) cons_sync();
+      if (cut_rows) cons_sync<CONS>();
 
       PF_STAMP(0);
       // ---- phase 2: rank by tot; per-prefix entries.  The rank only sets the staircase width of a row; when even the
       // last row keeps all nc1 candidates (few candidates: every frame of a confident model) no row is cut and the
       // prefixes keep their order.
       const float r_blank = F.rl[0];
-      for (int p = tid; p < np; p += BM_CONS) {
+      for (int p = tid; p < np; p += CONS) {
         const double mine = tot[p];
         int rk = p;
         if (cut_rows) {
@@ -888,7 +908,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         int J = W / (rk + 1) + 1;
         rowoff[rk] = cut_rows ? (J < nc1 ? J : nc1) : rk * nc1;
       }
-      cons_sync();
+      cons_sync<CONS>();
 
       PF_STAMP(1);
       // ---- phase 2b: exclusive scan of row widths (warp 0), only if some row is cut
@@ -909,7 +929,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         }
         if (lane == 0) sc->n_e3 = carry;
       }
-      cons_sync();
+      cons_sync<CONS>();
       }
 
       PF_STAMP(2);
@@ -917,8 +937,20 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       const int n_e3 = cut_rows ? sc->n_e3 : np * nc1;
       const int ncand = 2 * np + n_e3;
       SSD_ASSERT(ncand <= NCAND);
+      // descriptor of candidate k: (prefix << 8) | label, label 0 = blank-ended entry, 0xFE = char-ended entry.
+      // The LM kernel's rows are uniform, so it derives the descriptor from the index instead of storing it.
+      auto desc_of = [&](int k) -> uint32_t {
+        if constexpr (LM) {
+          if (k < np) return (uint32_t)k << 8;
+          if (k < 2 * np) return ((uint32_t)(k - np) << 8) | 0xFEu;
+          const int q = k - 2 * np, row = q / nc1;
+          return ((uint32_t)row << 8) | (uint32_t)F.cs[q - row * nc1];
+        } else {
+          return cdesc[k];
+        }
+      };
       double m_loc = neg_inf();
-      for (int k = tid; k < ncand; k += BM_CONS) {
+      for (int k = tid; k < ncand; k += CONS) {
         double s;
         uint32_t d;
         if (k < np) {
@@ -930,13 +962,21 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           d = ((uint32_t)p << 8) | 0xFEu;  // char-ended entry of prefix p
         } else {
           const int q = k - 2 * np;
-          int lo = 0, hi = np - 1;  // last row with rowoff <= q
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (rowoff[mid] <= q) lo = mid; else hi = mid - 1;
+          int lo, col;
+          if ((LM || SSD_BEAM_ROWDIV) && !cut_rows) {  // uniform rows of nc1 proposals in prefix order
+            lo = q / nc1;
+            col = q - lo * nc1;
+          } else {
+            lo = 0;
+            int hi = np - 1;  // last row with rowoff <= q
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (rowoff[mid] <= q) lo = mid; else hi = mid - 1;
+            }
+            col = q - rowoff[lo];
           }
-          const int p = rank2p[lo];
-          const int c = (int)F.cs[q - rowoff[lo]];
+          const int p = cut_rows ? rank2p[lo] : lo;
+          const int c = (int)F.cs[col];
           const int e = A.last[p];
           s = neg_inf();
           if (!(c == space_lbl && e == space_lbl)) {  // absorbed space is not an extension
@@ -950,8 +990,10 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           }
           d = ((uint32_t)p << 8) | (uint32_t)c;
         }
-        cscore[k] = s;
-        cdesc[k] = d;
+        if constexpr (!LM) {
+          cscore[k] = s;
+          cdesc[k] = d;
+        }
         if constexpr (LM) {
           if (s != -INFINITY) {
             const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
@@ -974,32 +1016,32 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       }
       m_loc = warp_max_d(m_loc);
       if (lane == 0) sc->wmax[warp] = m_loc;
-      cons_sync();
+      cons_sync<CONS>();
 
       PF_STAMP(3);
       // ---- phase 4a: block max (the warps' maxima were left in sc->wmax by phase 3)
       double cutoff;
       {
         double m = sc->wmax[0];
-        for (int w = 1; w < BM_CONS / 32; ++w) m = sc->wmax[w] > m ? sc->wmax[w] : m;
+        for (int w = 1; w < CONS / 32; ++w) m = sc->wmax[w] > m ? sc->wmax[w] : m;
         cutoff = m + (double)s_prune;
       }
       PF_STAMP(4);
       // ---- phase 4b: compact entries that survive the relative prune (order preserved)
       int n_alive;
       {
-        // ballots over chunks of BM_CONS.  (One scan over per-thread runs of candidates -- two barriers however many
+        // ballots over chunks of CONS.  (One scan over per-thread runs of candidates -- two barriers however many
         // candidates -- measured 4 % slower on config 3: the scan's five dependent shuffles cost more than the barriers.)
         int running = 0;
-        for (int base_k = 0; base_k < ncand; base_k += BM_CONS) {
+        for (int base_k = 0; base_k < ncand; base_k += CONS) {
           const int k = base_k + tid;
           const bool alive = k < ncand && rscore[k] >= cutoff && rscore[k] != -INFINITY;
           const unsigned m = __ballot_sync(FULL, alive);
           if (lane == 0) sc->wcnt[warp] = __popc(m);
-          cons_sync();
+          cons_sync<CONS>();
           int off = running, totc = 0;
 #pragma unroll
-          for (int w = 0; w < BM_CONS / 32; ++w) {
+          for (int w = 0; w < CONS / 32; ++w) {
             const int c = sc->wcnt[w];
             if (w < warp) off += c;
             totc += c;
@@ -1010,11 +1052,11 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
             if (pos < W) sel[pos] = k;
           }
           running += totc;
-          if (base_k + BM_CONS < ncand) cons_sync();  // wcnt is rewritten by the next chunk
+          if (base_k + CONS < ncand) cons_sync<CONS>();  // wcnt is rewritten by the next chunk
         }
         n_alive = running;
       }
-      cons_sync();
+      cons_sync<CONS>();
       const int n_sel = n_alive < W ? n_alive : W;
       PF_STAMP(5);
       // ---- phase 4c: the W best alive entries go to sel[rank].
@@ -1026,18 +1068,18 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       // slot and node numbers, and the best entry per history key is found by score below, not by rank.)
       if (n_alive > W) {
         hk_dirty = true;  // the bucket cut works in the memory the history-key table lives in
-        for (int i = tid; i < 256; i += BM_CONS) hist[i] = 0;
+        for (int i = tid; i < 256; i += CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
-        cons_sync();
+        cons_sync<CONS>();
         const double top = cutoff - (double)s_prune;
         const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
-        for (int i = tid; i < n_alive; i += BM_CONS) {
+        for (int i = tid; i < n_alive; i += CONS) {
           int b = (int)((top - rscore[aidx[i]]) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
-          abkt[i] = b;
+          abkt[i] = (bk_t)b;
           atomicAdd(&hist[b], 1);
         }
-        cons_sync();
+        cons_sync<CONS>();
         if (warp == 0) {  // boundary bucket: first one where the running count reaches W
           int c[8], tot = 0;
 #pragma unroll
@@ -1057,13 +1099,13 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
             }
           }
         }
-        cons_sync();
+        cons_sync<CONS>();
         const int beta = sc->beta, need = W - sc->c0;
-        for (int i = tid; i < n_alive; i += BM_CONS)
-          if (abkt[i] == beta) blist[atomicAdd(&sc->n_b, 1)] = i;
-        cons_sync();
+        for (int i = tid; i < n_alive; i += CONS)
+          if (abkt[i] == beta) blist[atomicAdd(&sc->n_b, 1)] = (bk_t)i;
+        cons_sync<CONS>();
         const int m = sc->n_b;
-        for (int t = tid; t < m; t += BM_CONS) {
+        for (int t = tid; t < m; t += CONS) {
           const int i = blist[t];
           const double mine = rscore[aidx[i]];
           int rk = 0;
@@ -1072,21 +1114,21 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
             const double o = rscore[aidx[j]];
             rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
           }
-          abkt[i] = rk < need ? -1 : 256;  // in / out
+          abkt[i] = (bk_t)(rk < need ? -1 : 256);  // in / out
         }
-        cons_sync();
+        cons_sync<CONS>();
         // compact the W survivors, alive order preserved
         {
           int running = 0;
-          for (int base_i = 0; base_i < n_alive; base_i += BM_CONS) {
+          for (int base_i = 0; base_i < n_alive; base_i += CONS) {
             const int i = base_i + tid;
             const bool in = i < n_alive && abkt[i] < beta;
             const unsigned mk = __ballot_sync(FULL, in);
             if (lane == 0) sc->wcnt[warp] = __popc(mk);
-            cons_sync();
+            cons_sync<CONS>();
             int off = running, totc = 0;
 #pragma unroll
-            for (int w = 0; w < BM_CONS / 32; ++w) {
+            for (int w = 0; w < CONS / 32; ++w) {
               const int cw = sc->wcnt[w];
               if (w < warp) off += cw;
               totc += cw;
@@ -1096,13 +1138,13 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
               bidx[pos] = aidx[i];
             }
             running += totc;
-            cons_sync();
+            cons_sync<CONS>();
           }
           SSD_ASSERT(running == W);
         }
-        for (int i = tid; i < W; i += BM_CONS) sel[i] = bidx[i];
+        for (int i = tid; i < W; i += CONS) sel[i] = bidx[i];
       }
-      cons_sync();
+      cons_sync<CONS>();
 
       PF_STAMP(6);
       // ---- phase 5: history keys, then keep the best entry per key.
@@ -1114,15 +1156,15 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       // the same loop that computes them: three barriers for the phase instead of five.
       const bool small_sel = n_sel <= P.small_sel;  // a handful of entries (narrow beams): compare directly, one pass
       if (hk_dirty && !small_sel) {
-        for (int i = tid; i < HKS; i += BM_CONS) {
+        for (int i = tid; i < HKS; i += CONS) {
           hk_keys[i] = 0ull;
           hk_best[i] = 0ull;
           hk_idx[i] = 0x7fffffff;
         }
-        cons_sync();
+        cons_sync<CONS>();
       }
-      for (int r = tid; r < n_sel; r += BM_CONS) {
-        const uint32_t d = cdesc[sel[r]];
+      for (int r = tid; r < n_sel; r += CONS) {
+        const uint32_t d = desc_of(sel[r]);
         const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
         uint64_t hl = A.hl[p], ho = A.ho[p];
         int lc;
@@ -1148,16 +1190,16 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
         }
       }
-      for (int p = tid; p < np; p += BM_CONS) keepf[p] = 0;
-      cons_sync();
+      for (int p = tid; p < np; p += CONS) keepf[p] = 0;
+      cons_sync<CONS>();
       if (!small_sel) {
-        for (int r = tid; r < n_sel; r += BM_CONS) {
+        for (int r = tid; r < n_sel; r += CONS) {
           const int s_ = sel_slot[r];
           if (order_key(rscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
         }
-        cons_sync();
+        cons_sync<CONS>();
       }
-      for (int r = tid; r < n_sel; r += BM_CONS) {
+      for (int r = tid; r < n_sel; r += CONS) {
         int keep;
         if (small_sel) {
           const uint64_t hk = sel_hk[r];
@@ -1171,7 +1213,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         } else {
           keep = hk_idx[sel_slot[r]] == sel[r] ? 1 : 0;
         }
-        const uint32_t d = cdesc[sel[r]];
+        const uint32_t d = desc_of(sel[r]);
         const int c = (int)(d & 0xFFu);
         if (keep && (c == 0 || c == 0xFE)) {
           atomicOr(&keepf[d >> 8], c == 0 ? 1 : 2);
@@ -1181,7 +1223,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           sel_keep[r] = keep;
         }
       }
-      cons_sync();
+      cons_sync<CONS>();
 
       PF_STAMP(7);
       // ---- phase 6a: slots.  warp 0 scans surviving old prefixes, warp 1 the new ones.
@@ -1196,7 +1238,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         }
         if (lane == 0) sc->n_keep_old = carry;
       }
-      if (warp == (BM_CONS > 32 ? 1 : 0)) {
+      if (warp == (CONS > 32 ? 1 : 0)) {
         int carry = 0;
         for (int i0 = 0; i0 < n_sel; i0 += 32) {
           const int i = i0 + lane;
@@ -1207,22 +1249,22 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         }
         if (lane == 0) sc->n_new = carry;
       }
-      for (int i = tid; i < TS; i += BM_CONS) tkeys[i] = 0ull;
+      for (int i = tid; i < TS; i += CONS) tkeys[i] = 0ull;
       if (!small_sel) {  // the history-key table goes back to zero for its next use (its last read is behind the barrier above)
-        for (int i = tid; i < HKS; i += BM_CONS) {
+        for (int i = tid; i < HKS; i += CONS) {
           hk_keys[i] = 0ull;
           hk_best[i] = 0ull;
           hk_idx[i] = 0x7fffffff;
         }
       }
       hk_dirty = false;
-      cons_sync();
+      cons_sync<CONS>();
 
       PF_STAMP(8);
       // ---- phase 6b: write the next generation and its hash table
       const int n_old = sc->n_keep_old, n_new = sc->n_new;
       SSD_ASSERT(n_old + n_new >= 1 && n_old + n_new <= W);
-      for (int p = tid; p < np; p += BM_CONS) {
+      for (int p = tid; p < np; p += CONS) {
         const int s = oslot[p];
         if (s < 0) continue;
         N.H[s] = A.H[p]; N.Hpar[s] = A.Hpar[p]; N.Hstrip[s] = A.Hstrip[p];
@@ -1236,19 +1278,22 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
           for (int j = 0; j < CX; ++j) { ctxN[s * CX + j] = ctxA[p * CX + j]; hwN[s * CX + j] = hwA[p * CX + j]; }
         }
       }
-      for (int r = tid; r < n_sel; r += BM_CONS) {
+      for (int r = tid; r < n_sel; r += CONS) {
         const int j = sel_slot[r];
         if (j < 0) continue;
         const int s = n_old + j;
         const int k = sel[r];
-        const uint32_t d = cdesc[k];
+        const uint32_t d = desc_of(k);
         const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
         const uint64_t h = hmix(A.H[p], (uint32_t)c);
         N.H[s] = h; N.Hpar[s] = A.H[p];
         if (c == space_lbl) { N.Hstrip[s] = A.H[p]; N.hl[s] = A.ho[p]; N.ho[s] = 0ull; }
         else { N.Hstrip[s] = h; N.hl[s] = A.hl[p]; N.ho[s] = hmix(A.ho[p], (uint32_t)c); }
         N.last[s] = c; N.len[s] = A.len[p] + 1;
-        N.sb[s] = neg_inf(); N.snb[s] = cscore[k];
+        // the beam carries the ACOUSTIC score on; the LM kernel kept only the ranking score and recomputes it (a
+        // selected proposal is never a folded or absorbed one: those rank -inf)
+        N.sb[s] = neg_inf();
+        N.snb[s] = LM ? ((c == A.last[p]) ? A.sb[p] : tot[p]) + (double)F.rl[c] : cscore[k];
         const unsigned nd = node0 + (unsigned)j;
         SSD_ASSERT((int64_t)nd < P.node_cap);
         N.node[s] = nd;
@@ -1284,7 +1329,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
       pf_gen += pf_t1 - pf_t0;
       ++pf_ngen;
 #endif
-      bar_sync(BAR_FRAME, BM_THREADS);  // next generation, table, and frame t+1 record are all visible
+      bar_sync(BAR_FRAME, THREADS);  // next generation, table, and frame t+1 record are all visible
 #ifdef SSD_BEAM_PROF
       pf_wait += clock64() - pf_t1;
 #endif
@@ -1305,9 +1350,9 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
     if (!producer) {
       const PrefixView A = prefix_view(gen0, g, gs8, gs4);
       const int np = sc->np;
-      for (int p = tid; p < np; p += BM_CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
-      cons_sync();
-      for (int p = tid; p < np; p += BM_CONS) {
+      for (int p = tid; p < np; p += CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
+      cons_sync<CONS>();
+      for (int p = tid; p < np; p += CONS) {
         // group = prefixes with equal text after dropping a trailing space
         const uint64_t hs = A.Hstrip[p];
         double f = neg_inf();
@@ -1344,7 +1389,7 @@ __global__ void __launch_bounds__(BM_THREADS, LM ? 2 : SSD_BEAM_MINCTAS) beam_ke
         }
         newb[p] = (rep == p) ? f : neg_inf();  // one representative per group competes
       }
-      cons_sync();
+      cons_sync<CONS>();
       if (tid == 0) {
         int best = 0;
         for (int p = 1; p < np; ++p)
@@ -1378,7 +1423,7 @@ static int beam_grid(int64_t B, size_t smem, bool lm) {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (lm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<true>, BM_THREADS, smem);
+  if (lm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<true>, BM_LM_THREADS, smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<false>, BM_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   const int64_t g = (int64_t)sms * per_sm;
@@ -1498,7 +1543,7 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaMemsetAsync: %s", cudaGetErrorString(e));
 #endif
   if (lm) {
-    SSD_LAUNCH(beam_kernel<true>, (unsigned)grid, BM_THREADS, smem, stream, P);
+    SSD_LAUNCH(beam_kernel<true>, (unsigned)grid, BM_LM_THREADS, smem, stream, P);
   } else {
     SSD_LAUNCH(beam_kernel<false>, (unsigned)grid, BM_THREADS, smem, stream, P);
   }
