@@ -55,6 +55,35 @@ namespace ssd {
 #define SSD_BEAM_ROWDIV 0  // no-LM kernel, uniform proposal rows: row = index / width instead of the binary search over row offsets
                            // (measured on config 3: 184.1 k against 187.1 k utterances/s confident, flat equal; the LM kernel always divides)
 #endif
+#ifndef SSD_BEAM_UNROLL1
+#define SSD_BEAM_UNROLL1 1
+#endif
+#if SSD_BEAM_UNROLL1 && !defined(SSD_EMU)
+#define SSD_NO_UNROLL _Pragma("unroll 1")
+#else
+#define SSD_NO_UNROLL
+#endif
+#ifndef SSD_BEAM_UNROLL1_INNER
+#define SSD_BEAM_UNROLL1_INNER 1
+#endif
+#if SSD_BEAM_UNROLL1_INNER && !defined(SSD_EMU)
+#define SSD_NO_UNROLL_INNER _Pragma("unroll 1")
+#else
+#define SSD_NO_UNROLL_INNER
+#endif
+// the two rank-counting loops only flat posteriors reach (staircase ranks, boundary bucket of the W-best cut): compute
+// loops that gain from the compiler's unrolling (flat config 3: 141 k utterances/s unrolled, 127 k rolled)
+#ifndef SSD_BEAM_UNROLL1_FLAT
+#define SSD_BEAM_UNROLL1_FLAT 0
+#endif
+#if SSD_BEAM_UNROLL1_FLAT && !defined(SSD_EMU)
+#define SSD_NO_UNROLL_FLAT _Pragma("unroll 1")
+#else
+#define SSD_NO_UNROLL_FLAT
+#endif
+#ifndef SSD_BEAM_LSE_INLINE
+#define SSD_BEAM_LSE_INLINE 1
+#endif
 #ifndef SSD_BEAM_CONS
 #define SSD_BEAM_CONS 64
 #endif
@@ -142,7 +171,11 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 // fp64 logaddexp in upstream's form: hi + log(1 + exp(lo - hi)).  Inlined on purpose: one shared out-of-line copy
 // (the fp64 log and exp are ~180 SASS instructions, four copies) cut the registers from 80 to 63 but measured 5 %
 // slower at 8 CTAs per SM (185k against 194k utterances/s on config 3, confident input).
+#if SSD_BEAM_LSE_INLINE
 __device__ __forceinline__ double lse2(double a, double b) {
+#else
+__device__ __noinline__ double lse2(double a, double b) {
+#endif
   const double hi = a >= b ? a : b, lo = a >= b ? b : a;
   if (lo == -INFINITY) return hi;
   return hi + log(1.0 + exp(lo - hi));
@@ -295,10 +328,23 @@ struct Scal {
 // ------------------------------------------------------------------ producer: condition one frame
 // All 32 lanes; labels k = lane, lane+32, ...  Mirrors ctc.py:76-87 and decode_beams' fp32
 // log-softmax + clip, then builds the candidate set {k: r_k >= tmin} | {argmax}.
-__device__ void condition_frame(const float* __restrict__ row, const BeamParams& P, float bias, float tmin,
+// PER = label groups of 32 the warp walks (2 for the reference's 47 labels, SSD_MAX_VOCAB / 32 in general); out of line:
+// one call per frame, and only the instantiation in use occupies the instruction cache.
+#ifndef SSD_BEAM_COND_INLINE
+#define SSD_BEAM_COND_INLINE 0
+#endif
+struct CondArgs {
+  int VL, blank, pad;
+};
+template <int PER>
+#if SSD_BEAM_COND_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void condition_frame_n(const float* __restrict__ row, const CondArgs P, float bias, float tmin,
                                 const int* __restrict__ lab2voc, FrameRec fr, int* nc1_out) {
   const int lane = lane_id();
-  constexpr int PER = SSD_MAX_VOCAB / 32;
   float x[PER];
   float m = -INFINITY;
 #pragma unroll
@@ -391,6 +437,16 @@ __device__ void condition_frame(const float* __restrict__ row, const BeamParams&
     if (cand[i]) fr.cs[rank[i]] = (unsigned char)(lane + 32 * i);
   if (lane == 0) *nc1_out = cnt;
   __syncwarp();
+}
+__device__ __forceinline__ void condition_frame(const float* __restrict__ row, const BeamParams& P, float bias, float tmin,
+                                                const int* __restrict__ lab2voc, FrameRec fr, int* nc1_out) {
+  const CondArgs a = {P.VL, P.blank, P.pad};
+#if SSD_BEAM_COND_INLINE
+  condition_frame_n<SSD_MAX_VOCAB / 32>(row, a, bias, tmin, lab2voc, fr, nc1_out);
+#else
+  if (P.VL <= 64) condition_frame_n<2>(row, a, bias, tmin, lab2voc, fr, nc1_out);
+  else condition_frame_n<SSD_MAX_VOCAB / 32>(row, a, bias, tmin, lab2voc, fr, nc1_out);
+#endif
 }
 
 // ------------------------------------------------------------------ hash table (shared memory)
@@ -625,6 +681,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
   }
   __syncthreads();
   int space_lbl = -1;
+  SSD_NO_UNROLL_INNER
   for (int k = 1; k < VL; ++k)
     if (lab2voc[k] == space_lbl_vocab) space_lbl = k;
 
@@ -679,9 +736,12 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       unsigned long long slots = 1024ull;
       while (slots < 2ull * (unsigned long long)len * (unsigned long long)W && (int64_t)slots < P.seen_cap) slots <<= 1;
       seen_mask = slots - 1ull;
+      SSD_NO_UNROLL
       for (unsigned long long i = (unsigned long long)tid; i < slots; i += THREADS) seen[i] = 0ull;
     }
+    SSD_NO_UNROLL
     for (int i = tid; i < TS; i += THREADS) tkeys[i] = 0ull;
+    SSD_NO_UNROLL
     for (int i = tid; i < HKS; i += THREADS) {
       hk_keys[i] = 0ull;
       hk_best[i] = 0ull;
@@ -810,6 +870,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         const double rb = (double)F.rl[c1];
         double m = neg_inf();
         bool general = false;
+        SSD_NO_UNROLL
         for (int p = tid; p < np; p += CONS) {
           double v;
           uint32_t lc;
@@ -833,17 +894,20 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         double mm = sc->wmax[0];
         for (int w = 1; w < CONS / 32; ++w) mm = sc->wmax[w] > mm ? sc->wmax[w] : mm;
         const double cut = mm + (double)s_prune;
+        SSD_NO_UNROLL
         for (int p = tid; p < np; p += CONS) {
           double v = newb[p];
           if constexpr (LM) v += lm_of(p);
           if (!(v >= cut) || v == -INFINITY) general = true;
           const uint64_t hk = sel_hk[p];
+          SSD_NO_UNROLL_INNER
           for (int q = 0; q < np; ++q)
             if (q != p && sel_hk[q] == hk) general = true;
         }
         if (general) sc->n_b = 1;
         cons_sync<CONS>();
         if (sc->n_b == 0) {
+          SSD_NO_UNROLL
           for (int p = tid; p < np; p += CONS) {
             if (blank_only) {
               A.sb[p] = newb[p];
@@ -871,6 +935,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // ---- phase 1: tot, parent slot.  (When no staircase row is cut -- see phase 2 -- nobody needs another prefix's
       // tot before phase 3 except for the parent's, which is then recomputed on the spot: phases 1 and 2 share a barrier.)
       const bool cut_rows = !LM && nc1 > W / np + 1;  // under LM scores the staircase bound does not hold: full rows
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) {
         tot[p] = lse2(A.sb[p], A.snb[p]);
         par[p] = table_find(tkeys, tvals, tmask, A.Hpar[p]);
@@ -882,11 +947,13 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // last row keeps all nc1 candidates (few candidates: every frame of a confident model) no row is cut and the
       // prefixes keep their order.
       const float r_blank = F.rl[0];
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) {
         const double mine = tot[p];
         int rk = p;
         if (cut_rows) {
           rk = 0;
+          SSD_NO_UNROLL_FLAT
           for (int q = 0; q < np; ++q) {
             const double o = tot[q];
             rk += (o > mine || (o == mine && q < p)) ? 1 : 0;
@@ -915,6 +982,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       if (cut_rows) {
       if (warp == 0) {
         int carry = 0;
+        SSD_NO_UNROLL_INNER
         for (int i0 = 0; i0 < np; i0 += 32) {
           const int i = i0 + lane;
           const int v = i < np ? rowoff[i] : 0;
@@ -950,6 +1018,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
       };
       double m_loc = neg_inf();
+      SSD_NO_UNROLL
       for (int k = tid; k < ncand; k += CONS) {
         double s;
         uint32_t d;
@@ -1033,6 +1102,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         // ballots over chunks of CONS.  (One scan over per-thread runs of candidates -- two barriers however many
         // candidates -- measured 4 % slower on config 3: the scan's five dependent shuffles cost more than the barriers.)
         int running = 0;
+        SSD_NO_UNROLL
         for (int base_k = 0; base_k < ncand; base_k += CONS) {
           const int k = base_k + tid;
           const bool alive = k < ncand && rscore[k] >= cutoff && rscore[k] != -INFINITY;
@@ -1068,11 +1138,13 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // slot and node numbers, and the best entry per history key is found by score below, not by rank.)
       if (n_alive > W) {
         hk_dirty = true;  // the bucket cut works in the memory the history-key table lives in
+        SSD_NO_UNROLL
         for (int i = tid; i < 256; i += CONS) hist[i] = 0;
         if (tid == 0) sc->n_b = 0;
         cons_sync<CONS>();
         const double top = cutoff - (double)s_prune;
         const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
+        SSD_NO_UNROLL
         for (int i = tid; i < n_alive; i += CONS) {
           int b = (int)((top - rscore[aidx[i]]) * scale);
           b = b < 0 ? 0 : (b > 255 ? 255 : b);
@@ -1101,14 +1173,17 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
         cons_sync<CONS>();
         const int beta = sc->beta, need = W - sc->c0;
+        SSD_NO_UNROLL
         for (int i = tid; i < n_alive; i += CONS)
           if (abkt[i] == beta) blist[atomicAdd(&sc->n_b, 1)] = (bk_t)i;
         cons_sync<CONS>();
         const int m = sc->n_b;
+        SSD_NO_UNROLL
         for (int t = tid; t < m; t += CONS) {
           const int i = blist[t];
           const double mine = rscore[aidx[i]];
           int rk = 0;
+          SSD_NO_UNROLL_FLAT
           for (int u = 0; u < m; ++u) {
             const int j = blist[u];
             const double o = rscore[aidx[j]];
@@ -1120,6 +1195,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         // compact the W survivors, alive order preserved
         {
           int running = 0;
+          SSD_NO_UNROLL
           for (int base_i = 0; base_i < n_alive; base_i += CONS) {
             const int i = base_i + tid;
             const bool in = i < n_alive && abkt[i] < beta;
@@ -1142,6 +1218,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           }
           SSD_ASSERT(running == W);
         }
+        SSD_NO_UNROLL
         for (int i = tid; i < W; i += CONS) sel[i] = bidx[i];
       }
       cons_sync<CONS>();
@@ -1156,6 +1233,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // the same loop that computes them: three barriers for the phase instead of five.
       const bool small_sel = n_sel <= P.small_sel;  // a handful of entries (narrow beams): compare directly, one pass
       if (hk_dirty && !small_sel) {
+        SSD_NO_UNROLL
         for (int i = tid; i < HKS; i += CONS) {
           hk_keys[i] = 0ull;
           hk_best[i] = 0ull;
@@ -1163,6 +1241,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
         cons_sync<CONS>();
       }
+      SSD_NO_UNROLL
       for (int r = tid; r < n_sel; r += CONS) {
         const uint32_t d = desc_of(sel[r]);
         const int p = (int)(d >> 8), c = (int)(d & 0xFFu);
@@ -1190,21 +1269,25 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           sel_slot[r] = s_;  // remembered for the two passes below (sel_slot is rewritten in phase 6a)
         }
       }
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) keepf[p] = 0;
       cons_sync<CONS>();
       if (!small_sel) {
+        SSD_NO_UNROLL
         for (int r = tid; r < n_sel; r += CONS) {
           const int s_ = sel_slot[r];
           if (order_key(rscore[sel[r]]) == hk_best[s_]) atomicMin(&hk_idx[s_], sel[r]);
         }
         cons_sync<CONS>();
       }
+      SSD_NO_UNROLL
       for (int r = tid; r < n_sel; r += CONS) {
         int keep;
         if (small_sel) {
           const uint64_t hk = sel_hk[r];
           const double mine = rscore[sel[r]];
           keep = 1;
+          SSD_NO_UNROLL_INNER
           for (int q = 0; q < n_sel; ++q) {
             if (q == r || sel_hk[q] != hk) continue;
             const double o = rscore[sel[q]];
@@ -1229,6 +1312,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // ---- phase 6a: slots.  warp 0 scans surviving old prefixes, warp 1 the new ones.
       if (warp == 0) {
         int carry = 0;
+        SSD_NO_UNROLL_INNER
         for (int i0 = 0; i0 < np; i0 += 32) {
           const int i = i0 + lane;
           const bool f = i < np && keepf[i] != 0;
@@ -1240,6 +1324,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       }
       if (warp == (CONS > 32 ? 1 : 0)) {
         int carry = 0;
+        SSD_NO_UNROLL_INNER
         for (int i0 = 0; i0 < n_sel; i0 += 32) {
           const int i = i0 + lane;
           const bool f = i < n_sel && sel_keep[i] != 0;
@@ -1249,8 +1334,10 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
         if (lane == 0) sc->n_new = carry;
       }
+      SSD_NO_UNROLL
       for (int i = tid; i < TS; i += CONS) tkeys[i] = 0ull;
       if (!small_sel) {  // the history-key table goes back to zero for its next use (its last read is behind the barrier above)
+        SSD_NO_UNROLL
         for (int i = tid; i < HKS; i += CONS) {
           hk_keys[i] = 0ull;
           hk_best[i] = 0ull;
@@ -1264,6 +1351,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // ---- phase 6b: write the next generation and its hash table
       const int n_old = sc->n_keep_old, n_new = sc->n_new;
       SSD_ASSERT(n_old + n_new >= 1 && n_old + n_new <= W);
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) {
         const int s = oslot[p];
         if (s < 0) continue;
@@ -1278,6 +1366,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           for (int j = 0; j < CX; ++j) { ctxN[s * CX + j] = ctxA[p * CX + j]; hwN[s * CX + j] = hwA[p * CX + j]; }
         }
       }
+      SSD_NO_UNROLL
       for (int r = tid; r < n_sel; r += CONS) {
         const int j = sel_slot[r];
         if (j < 0) continue;
@@ -1350,13 +1439,16 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
     if (!producer) {
       const PrefixView A = prefix_view(gen0, g, gs8, gs4);
       const int np = sc->np;
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) tot[p] = lse2(A.sb[p], A.snb[p]);
       cons_sync<CONS>();
+      SSD_NO_UNROLL
       for (int p = tid; p < np; p += CONS) {
         // group = prefixes with equal text after dropping a trailing space
         const uint64_t hs = A.Hstrip[p];
         double f = neg_inf();
         int rep = p;
+        SSD_NO_UNROLL_INNER
         for (int q = 0; q < np; ++q)
           if (A.Hstrip[q] == hs) {
             f = lse2(f, tot[q]);
@@ -1372,6 +1464,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
             const int* plenF = lplen_base + g * lm_gs4;
             const int* ctxF = lctx_base + g * lm_gs4;
             int q_open = -1, q_closed = -1;
+            SSD_NO_UNROLL_INNER
             for (int q = 0; q < np; ++q)
               if (A.Hstrip[q] == hs) {
                 if (plenF[q] > 0) q_open = q; else q_closed = q;
@@ -1392,6 +1485,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       cons_sync<CONS>();
       if (tid == 0) {
         int best = 0;
+        SSD_NO_UNROLL_INNER
         for (int p = 1; p < np; ++p)
           if (newb[p] > newb[best]) best = p;
         int n = A.len[best];

@@ -266,3 +266,33 @@ def test_lm_restatement_matches_upstream(golden_dir, tmp_path):
         assert [o[0] for o in out] == list(z[f"{name}.text"]), name
         np.testing.assert_allclose([o[1] for o in out], z[f"{name}.logit_score"], rtol=0, atol=1e-4, err_msg=name)
         np.testing.assert_allclose([o[2] for o in out], z[f"{name}.lm_score"], rtol=0, atol=1e-4, err_msg=name)
+
+
+@pytest.mark.parametrize("order", ["rev", "rnd:5"])
+def test_lm_kernel_schedule_independence(order, arpa3):
+    """Same transcripts and scores when the emulator visits threads in another order (a missing barrier around the LM
+    state, the ranking scores or the scored-text set would show here; compute-sanitizer is closed on the GPU pool)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np\n"
+        "from tests.emu import harness\n"
+        "from tests import lm_cases\n"
+        "from silent_speech_decoder_b200.data.vocab import Vocab\n"
+        "from silent_speech_decoder_b200.decoding import ctc, lm as plm\n"
+        "v = Vocab.default(); text, space = ctc._beam_label_strings(v)\n"
+        "keep = [i for i in range(v.size) if i not in {v.blank_id, v.pad_id}]\n"
+        f"tab = plm.build_tables({arpa3!r}, [''] + [text[i] for i in keep], 0.6, 0.3)\n"
+        "lp, ln = lm_cases.spelled_log_probs(lm_cases.SENTENCES[:4], 60, seed=9)\n"
+        "(ids, sc), = harness.beam_lm(harness.library(), lp, [60, 51, 60, 44], v.blank_id, v.pad_id, space, tab, [(25, -10.0, 0.0, -5.0)])\n"
+        "print(ids, [round(float(s), 9) for s in sc])\n"
+    )
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for o in ("fwd", order):
+        r = subprocess.run([sys.executable, "-c", code], cwd=repo, env={**os.environ, "SSD_EMU_ORDER": o, "PYTHONPATH": repo},
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and "[[" in outs[0]
