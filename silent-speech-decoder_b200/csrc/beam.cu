@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
     __syncthreads();
 
     int g = 0;  // current prefix generation
+    bool hk_clean = false;  // the live prefixes are known to have pairwise different history keys (uniform over the consumers)
 #ifdef SSD_BEAM_PROF
     long long pf_prod = 0, pf_fast = 0, pf_gen = 0, pf_wait = 0;
     int pf_nfast = 0, pf_ngen = 0;
@@ -865,6 +866,10 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       // snb + r_c: the blank entry is -inf, the extension P+c needs blank-ended mass and is -inf, the parent's
       // contribution is the parent's blank-ended mass and is -inf, and lse2(x, -inf) = x.  Same in-place update.
       const bool repeat_cand = nc1 == 1 && F.rl[0] == -INFINITY;
+      // "No two share a history key": every entry of such a frame has the same last char, so two keys are equal iff the
+      // prefixes' (closed words, open word) parts are -- a property of the prefix SET, which in-place frames do not
+      // change.  The O(np^2) comparison (a fifth of the kernel's instructions on confident input) is therefore made
+      // once per generation, by the first in-place frame after a general one (hk_clean).
       if (blank_only || repeat_cand) {
         const int c1 = repeat_cand ? (int)F.cs[0] : 0;
         const double rb = (double)F.rl[c1];
@@ -885,7 +890,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           newb[p] = v;
           if constexpr (LM) v += lm_of(p);  // the cut below is on the ranking score
           m = v > m ? v : m;
-          sel_hk[p] = hist_key(A.hl[p], A.ho[p], (int)lc, p, false, 0ull);  // phase 5's key of that entry
+          if (!hk_clean) sel_hk[p] = hist_key(A.hl[p], A.ho[p], (int)lc, p, false, 0ull);  // phase 5's key of that entry
         }
         m = warp_max_d(m);
         if (lane == 0) sc->wmax[warp] = m;
@@ -899,14 +904,17 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           double v = newb[p];
           if constexpr (LM) v += lm_of(p);
           if (!(v >= cut) || v == -INFINITY) general = true;
-          const uint64_t hk = sel_hk[p];
-          SSD_NO_UNROLL_INNER
-          for (int q = 0; q < np; ++q)
-            if (q != p && sel_hk[q] == hk) general = true;
+          if (!hk_clean) {
+            const uint64_t hk = sel_hk[p];
+            SSD_NO_UNROLL_INNER
+            for (int q = 0; q < np; ++q)
+              if (q != p && sel_hk[q] == hk) general = true;
+          }
         }
         if (general) sc->n_b = 1;
         cons_sync<CONS>();
         if (sc->n_b == 0) {
+          hk_clean = true;  // in particular no two keys were equal; holds until a general frame rebuilds the prefixes
           SSD_NO_UNROLL
           for (int p = tid; p < np; p += CONS) {
             if (blank_only) {
@@ -1412,6 +1420,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         sc->nodes_used = node0 + (unsigned)n_new;
       }
       g ^= 1;
+      hk_clean = false;
       PF_STAMP(9);
 #ifdef SSD_BEAM_PROF
       const long long pf_t1 = clock64();
