@@ -90,6 +90,10 @@ namespace ssd {
 constexpr int BM_CONS = SSD_BEAM_CONS;    // consumer threads (a per-frame phase rarely has more than ~100 items)
 constexpr int BM_THREADS = BM_CONS + 32;  // + producer warp
 constexpr int BM_CHUNK = SSD_BEAM_CHUNK;              // frames per TMA chunk (two buffers; shared memory decides the CTAs per SM)
+#ifndef SSD_BEAM_LM_CHUNK
+#define SSD_BEAM_LM_CHUNK 4
+#endif
+constexpr int BM_LM_CHUNK = SSD_BEAM_LM_CHUNK;        // the LM kernel: smaller chunks, it is after a fourth CTA per SM
 constexpr int BAR_CONS = 1;              // named barrier: consumers only
 constexpr int BAR_FRAME = 2;             // named barrier: consumers + producer, once per frame
 constexpr int LBL_NONE = 255;
@@ -268,8 +272,8 @@ __host__ __device__ inline int beam_hk_slots(int W, int NCAND) {
 // scratch shared by the bucket cut (bucket of each alive entry, boundary list: 2 x NCAND ints) and, after it, the
 // history-key table (key, best score, lowest index: 20 bytes per slot)
 __host__ __device__ inline size_t beam_scratch_bytes(int W, int NCAND, bool lm = false) {
-  // (the LM kernel, whose candidate capacity is 5-10 times larger, keeps the two lists as 16-bit values)
-  const size_t a = (lm ? 4 : 8) * (size_t)NCAND, b = 20 * (size_t)beam_hk_slots(W, NCAND);
+  // (the LM kernel, whose candidate capacity is 5-10 times larger, keeps the buckets as bytes and the list as 16-bit values)
+  const size_t a = (lm ? 3 : 8) * (size_t)NCAND, b = 20 * (size_t)beam_hk_slots(W, NCAND);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -292,14 +296,14 @@ __host__ __device__ inline size_t beam_smem_bytes(int W, int V, int VL, int TS, 
   s += al(8 * (size_t)TS) + al(4 * (size_t)TS);             // hash table
   s += al(8 * (size_t)NCAND);                               // candidate score (LM: the ranking score)
   if (lm_order == 0) s += al(4 * (size_t)NCAND);            // candidate desc (LM: rows are uniform, desc = f(index))
-  s += al(4 * (size_t)NCAND);                               // alive idx
+  s += al((lm_order > 0 ? 2 : 4) * (size_t)NCAND);          // alive idx (LM: 16-bit)
   s += beam_scratch_bytes(W, NCAND, lm_order > 0) + al(4 * 256);  // bucket cut scratch / history-key table, histogram
   s += al(4 * (size_t)(W + 1));                             // the W survivors of the bucket cut
   s += 3 * al(4 * (size_t)(W + 1));                         // sel (cand idx by rank), sel_keep, sel_slot
   s += al(8 * (size_t)(W + 1));                             // sel_hk
   s += 2 * (al(4 * (size_t)VL) + al(VL));                   // frame records: rl[VL], cs[VL] (x2)
   s += al(4 * (size_t)VL);                                  // lab2voc
-  s += 2 * al((size_t)BM_CHUNK * V * 4);                    // raw log-prob chunks
+  s += 2 * al((size_t)(lm_order > 0 ? BM_LM_CHUNK : BM_CHUNK) * V * 4);  // raw log-prob chunks
   s += 256;                                                 // scalars, mbarriers
   return s;
 }
@@ -570,7 +574,7 @@ __device__ inline bool seen_find(unsigned long long* tab, unsigned long long mas
 // LM = false: the no-LM search (the reference's configured path).  LM = true: the same search ranked by acoustic +
 // LM score; every `if constexpr (LM)` block below is absent from the no-LM instantiation.
 #ifndef SSD_BEAM_LM_MINCTAS
-#define SSD_BEAM_LM_MINCTAS 3
+#define SSD_BEAM_LM_MINCTAS 3  // 164 registers; shared memory (54.5 KB at width 50) then admits a fourth CTA, which the register file still holds
 #endif
 #ifndef SSD_BEAM_LM_CONS
 #define SSD_BEAM_LM_CONS 64  // consumer threads of the LM kernel (a frame has 5-10 times the candidates of a no-LM one)
@@ -604,10 +608,14 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
   int* tvals = (int*)carve(sp, 4 * TS);
   double* cscore = (double*)carve(sp, 8 * NCAND);  // LM: the RANKING score (acoustic + LM); the acoustic one is recomputed for survivors
   uint32_t* cdesc = LM ? nullptr : (uint32_t*)carve(sp, 4 * NCAND);
-  int* aidx = (int*)carve(sp, 4 * NCAND);
-  using bk_t = typename std::conditional<LM, short, int>::type;
+  using ai_t = typename std::conditional<LM, unsigned short, int>::type;  // candidate / alive indices (LM: capacity < 65536)
+  using bk_t = typename std::conditional<LM, unsigned char, int>::type;   // bucket of an alive entry
+  ai_t* aidx = (ai_t*)carve(sp, sizeof(ai_t) * NCAND);
   bk_t* abkt = (bk_t*)carve(sp, beam_scratch_bytes(WC, NCAND, LM));  // after the cut this scratch holds the history-key table
-  bk_t* blist = abkt + NCAND;
+  ai_t* blist = reinterpret_cast<ai_t*>(abkt + NCAND);
+  // bucket codes: no-LM int: bucket b, -1 = in, 256 = out.  LM byte: b + 1 with b <= 253, 0 = in, 255 = out
+  constexpr int BK_OFF = LM ? 1 : 0, BK_TOP = LM ? 253 : 255, BK_IN = LM ? 0 : -1, BK_OUT = LM ? 255 : 256;
+  constexpr int CHUNK = LM ? BM_LM_CHUNK : BM_CHUNK;
   int* hist = (int*)carve(sp, 4 * 256);
   int* bidx = (int*)carve(sp, 4 * (WC + 1));
   int* sel = (int*)carve(sp, 4 * (WC + 1));
@@ -626,8 +634,8 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
     return f;
   };
   int* lab2voc = (int*)carve(sp, 4 * VL);
-  float* const chunk0 = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
-  float* const chunk1 = (float*)carve(sp, (size_t)BM_CHUNK * P.V * 4);
+  float* const chunk0 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
+  float* const chunk1 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
   const ptrdiff_t chunk_stride = chunk1 - chunk0;
   auto chunk_buf = [&](int c) { return chunk0 + (c & 1) * chunk_stride; };
   Scal* sc = (Scal*)carve(sp, sizeof(Scal));
@@ -702,7 +710,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
     int64_t len64 = P.lengths[b];
     const int len = (int)(len64 < 0 ? 0 : (len64 > P.T ? P.T : len64));
     const float* base = P.lp + (int64_t)b * P.sb;
-    const int nchunks = (len + BM_CHUNK - 1) / BM_CHUNK;
+    const int nchunks = (len + CHUNK - 1) / CHUNK;
 
     // ---------------- initial beam: the empty prefix, blank-ended with score 0
     if (tid == 0) {
@@ -753,9 +761,9 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
 
     // ---------------- producer prologue: chunk 0 (+1 in flight), frame 0 record
     auto load_chunk = [&](int c) {  // producer warp
-      const int rows = min(BM_CHUNK, len - c * BM_CHUNK);
+      const int rows = min(CHUNK, len - c * CHUNK);
       float* dst = chunk_buf(c);
-      const float* src = base + (int64_t)c * BM_CHUNK * P.st;
+      const float* src = base + (int64_t)c * CHUNK * P.st;
       if (P.use_tma) {
         if (lane == 0) {
           const uint32_t bytes = (uint32_t)(rows * P.V * 4);
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         // -------- condition frame t+1 while the consumers work on frame t
         const int tn = t + 1;
         if (tn < len) {
-          const int c = tn / BM_CHUNK, r = tn - c * BM_CHUNK;
+          const int c = tn / CHUNK, r = tn - c * CHUNK;
           if (r == 0) {
             // chunk c-1 is fully consumed (its last frame was conditioned an iteration ago)
             if (c + 1 < nchunks) load_chunk(c + 1);
@@ -1126,7 +1134,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           }
           if (alive) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
-            aidx[pos] = k;
+            aidx[pos] = (ai_t)k;
             if (pos < W) sel[pos] = k;
           }
           running += totc;
@@ -1151,12 +1159,12 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         if (tid == 0) sc->n_b = 0;
         cons_sync<CONS>();
         const double top = cutoff - (double)s_prune;
-        const double scale = s_prune < 0.f ? 256.0 / -(double)s_prune : 0.0;
+        const double scale = s_prune < 0.f ? (double)(BK_TOP + 1) / -(double)s_prune : 0.0;
         SSD_NO_UNROLL
         for (int i = tid; i < n_alive; i += CONS) {
           int b = (int)((top - rscore[aidx[i]]) * scale);
-          b = b < 0 ? 0 : (b > 255 ? 255 : b);
-          abkt[i] = (bk_t)b;
+          b = b < 0 ? 0 : (b > BK_TOP ? BK_TOP : b);
+          abkt[i] = (bk_t)(b + BK_OFF);
           atomicAdd(&hist[b], 1);
         }
         cons_sync<CONS>();
@@ -1183,7 +1191,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         const int beta = sc->beta, need = W - sc->c0;
         SSD_NO_UNROLL
         for (int i = tid; i < n_alive; i += CONS)
-          if (abkt[i] == beta) blist[atomicAdd(&sc->n_b, 1)] = (bk_t)i;
+          if ((int)abkt[i] == beta + BK_OFF) blist[atomicAdd(&sc->n_b, 1)] = (ai_t)i;
         cons_sync<CONS>();
         const int m = sc->n_b;
         SSD_NO_UNROLL
@@ -1197,7 +1205,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
             const double o = rscore[aidx[j]];
             rk += (o > mine || (o == mine && j < i)) ? 1 : 0;
           }
-          abkt[i] = (bk_t)(rk < need ? -1 : 256);  // in / out
+          abkt[i] = (bk_t)(rk < need ? BK_IN : BK_OUT);  // in / out
         }
         cons_sync<CONS>();
         // compact the W survivors, alive order preserved
@@ -1206,7 +1214,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           SSD_NO_UNROLL
           for (int base_i = 0; base_i < n_alive; base_i += CONS) {
             const int i = base_i + tid;
-            const bool in = i < n_alive && abkt[i] < beta;
+            const bool in = i < n_alive && (int)abkt[i] < beta + BK_OFF;
             const unsigned mk = __ballot_sync(FULL, in);
             if (lane == 0) sc->wcnt[warp] = __popc(mk);
             cons_sync<CONS>();

@@ -35,6 +35,17 @@
 
 #include "ssd_common.cuh"
 
+// per-utterance set-up loops (executed once per utterance): rolled when SSD_F_SETUP_UNROLL1 is set, to keep them out of
+// the instruction cache's way (experiment knob)
+#ifndef SSD_F_SETUP_UNROLL1
+#define SSD_F_SETUP_UNROLL1 0
+#endif
+#if SSD_F_SETUP_UNROLL1 && !defined(SSD_EMU)
+#define SSD_F_SETUP_ROLL _Pragma("unroll 1")
+#else
+#define SSD_F_SETUP_ROLL
+#endif
+
 namespace ssd {
 
 constexpr int F_K = 8;          // frames per block = renormalisation and checkpoint interval
@@ -1389,12 +1400,14 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     }
 #endif
     if (P.late_worker && uiter > 0u) {  // the previous utterance's late worker had its rows over the sweeps' rings
+      SSD_F_SETUP_ROLL
       for (int i = tid; i < 2 * F_NP * F_K; i += F_THREADS) {
         const int blk = i / F_K, r = i - blk * F_K;
         unsigned char* base = smem + M.main_off + (size_t)(blk / F_NP) * M.main_bytes + (size_t)(blk % F_NP) * M.p_slot;
         reinterpret_cast<float*>(base)[P.V * F_KS + r] = 0.f;
       }
     }
+    SSD_F_SETUP_ROLL
     for (int j = tid; j < S; j += F_THREADS) {
       const int64_t y = P.targets[(int64_t)b * P.tgt_stride + j];
       if (y < 0 || y >= P.V) sc->skip = sc->uflag = 1;  // benign race: every writer stores 1
@@ -1406,25 +1419,31 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
     pl.b = b; pl.Tb = sc->T; pl.S = S; pl.L = 2 * S + 1;
     pl.NB = (pl.Tb + F_K - 1) / F_K;
     if (!skip) {
+      SSD_F_SETUP_ROLL
       for (int q = pl.NB + tid; q < P.nb_max; q += F_THREADS) {  // blocks this utterance does not have
         mbar_arrive(&blk_ready[q]);
         mbar_arrive(&blk_ready[q]);
       }
       // class histogram -> start offsets; position of every label in class-sorted order (stable)
+      SSD_F_SETUP_ROLL
       for (int v = tid; v < P.V; v += F_THREADS) {
         int c = 0;
+        SSD_F_SETUP_ROLL
         for (int j = 0; j < S; ++j) c += (lab[j] == v) ? 1 : 0;
         cls[v + 1] = c;
       }
       __syncthreads();
       if (tid == 0) {
         cls[0] = 0;
+        SSD_F_SETUP_ROLL
         for (int v = 0; v < P.V; ++v) cls[v + 1] += cls[v];
       }
       __syncthreads();
+      SSD_F_SETUP_ROLL
       for (int j = tid; j < S; j += F_THREADS) {
         const int y = lab[j];
         int k = 0;
+        SSD_F_SETUP_ROLL
         for (int i = 0; i < j; ++i) k += (lab[i] == y) ? 1 : 0;
         pos[j] = cls[y] + k;
       }
@@ -1434,7 +1453,9 @@ __global__ void __launch_bounds__(F_THREADS, 2) loss_fast_kernel(const FastParam
       // rows the sweeps never visit: frames beyond the input length
       if (P.grad) {
         float* g0 = P.grad + (int64_t)b * P.sb;
+        SSD_F_SETUP_ROLL
         for (int64_t r = pl.Tb + warp; r < P.T; r += F_THREADS / 32)
+          SSD_F_SETUP_ROLL
           for (int v = lane; v < P.V; v += 32) st_stream(g0 + r * P.st + v, 0.f);
       }
       int wslot = role >= 4 ? role - 4 : -1;  // worker buffer set: 0..F_W-1, F_W = the sweeps' ring space (late worker)
