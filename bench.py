@@ -543,14 +543,14 @@ def bench_decode(args, rank, world, dev, method: str, kind: str, n: int, T: int,
 
     peak, peak_src = measured_peak_gbs()
     achieved = DECODE_BYTES_PER_FRAME * n_local * T / (ms * 1e-3) / 1e9
-    kname = "beam_kernel" if method == "beam" else "greedy_kernel"
+    kname = "beam_kernel" if method == "beam" else "greedy_kernel"  # traffic.json keys; the kernel is ssd::beam_kernel<false>
     out = {
         "metric": f"ctc_{('beam' + str(width)) if method == 'beam' else 'greedy'}_decode_utterances_per_sec",
         "value": world * n_local / (ms * 1e-3), "unit": "utterances/s", "ms_per_step": ms, "dtype": "f64" if method == "beam" else "f32",
         "config": decode_config(method, n_local, T, kind, width, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(kname + (("_" + kind) if method == "beam" else ""), n_local * T), "peak_source": peak_src,
-                     "kernel": f"ssd::{kname}", "kernel_ms": ms, "algorithmic_bytes": DECODE_BYTES_PER_FRAME * n_local * T,
+                     "kernel": f"ssd::{kname}" + ("<false>" if method == "beam" else ""), "kernel_ms": ms, "algorithmic_bytes": DECODE_BYTES_PER_FRAME * n_local * T,
                      "note": "beam search is latency/issue bound, not HBM bound; see profiles/ for stall breakdown" if method == "beam" else ""},
         "gpu_launches": launches,
     }
@@ -619,7 +619,7 @@ def bench_beam_lm(args, rank, world, dev, n: int, T: int, width: int, seed: int)
         "config": {"workload": f"row f-4 at cfg3's shape: LM-fused beam decode of {n} utterances per GPU, T={T}, V=48, width {width}, prune -10, "
                                f"{c['order']}-gram word LM over {c['words']} words ({len(tables.ngram_prob)} n-grams), alpha {c['alpha']}, beta {c['beta']}",
                    "l2": f"input {n * T * 48 * 4 / 1e6:.0f} MB > 126 MB L2", "parallelism": f"dp{world} by utterance, no data-path collective"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic("beam_kernel_lm", n * T),
                      "peak_source": peak_src, "kernel": "ssd::beam_kernel<true>", "kernel_ms": ms,
                      "algorithmic_bytes": DECODE_BYTES_PER_FRAME * n * T,
                      "note": "latency/issue bound like the no-LM search; every beam proposes every candidate label (no staircase bound under LM scores)"},

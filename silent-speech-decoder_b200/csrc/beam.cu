@@ -914,13 +914,34 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           if (!(v >= cut) || v == -INFINITY) general = true;
           if (!hk_clean) {
             const uint64_t hk = sel_hk[p];
-            SSD_NO_UNROLL_INNER
-            for (int q = 0; q < np; ++q)
-              if (q != p && sel_hk[q] == hk) general = true;
+            if (!hk_dirty) {
+              // through the (zeroed) history-key table: whoever finds its key already there has a twin.  O(np) instead
+              // of O(np^2) comparisons -- at width 200 the pairwise scan was a third of a confident utterance's time.
+              int s_ = (int)(hk & (uint64_t)(HKS - 1));
+              int mine = -1;
+              int tries = 0;
+              for (; tries < HKS; ++tries) {  // bounded: the table has at least 2 np slots, so this never runs out
+                const unsigned long long old = atomicCAS(&hk_keys[s_], 0ull, (unsigned long long)hk);
+                if (old == 0ull) { mine = s_; break; }
+                if (old == (unsigned long long)hk) { general = true; break; }
+                s_ = (s_ + 1) & (HKS - 1);
+              }
+              if (tries == HKS) general = true;
+              sel_slot[p] = mine;
+            } else {  // the bucket cut left its scratch in the table's memory: compare pairwise
+              SSD_NO_UNROLL_INNER
+              for (int q = 0; q < np; ++q)
+                if (q != p && sel_hk[q] == hk) general = true;
+            }
           }
         }
         if (general) sc->n_b = 1;
         cons_sync<CONS>();
+        if (!hk_clean && !hk_dirty) {  // the table goes back to zero: every thread clears the slots it claimed
+          SSD_NO_UNROLL
+          for (int p = tid; p < np; p += CONS)
+            if (sel_slot[p] >= 0) hk_keys[sel_slot[p]] = 0ull;
+        }
         if (sc->n_b == 0) {
           hk_clean = true;  // in particular no two keys were equal; holds until a general frame rebuilds the prefixes
           SSD_NO_UNROLL
@@ -1359,8 +1380,8 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
           hk_best[i] = 0ull;
           hk_idx[i] = 0x7fffffff;
         }
+        hk_dirty = false;  // (a small selection leaves the table as it is: dirty stays dirty)
       }
-      hk_dirty = false;
       cons_sync<CONS>();
 
       PF_STAMP(8);
