@@ -22,6 +22,13 @@ Restated here [from memory of pyctcdecode 0.5.0 ``language_model.py`` / ``decode
 
 How the search uses them is in ``oracle/beam.py`` (``_score_lm``), including upstream's cache quirk: the
 end-of-sentence term is only added for texts that were never scored as closed texts before.
+
+Known uncertainty to settle when the upstream fixtures exist (``make_beam_golden_upstream.py``): the restatement
+follows the release whose score cache is keyed by the text alone (``Dict[str, ...]``).  The library's main branch
+keys it by ``(text, is_eos)``; under that variant EVERY final beam is re-scored with the ``</s>`` term, and a final
+beam whose text ends closed scores an EMPTY last word (an out-of-vocabulary word to kenlm: ``<unk>`` + the unk offset).
+If the fixtures disagree on end-of-utterance scores, this is the first place to look; the per-frame search is the
+same under both.
 """
 
 from __future__ import annotations
