@@ -326,7 +326,7 @@ struct Scal {
   int n_new;
   int utt;
   unsigned nodes_used;
-  int wcnt[4];
+  int wcnt[2][4];  // per-warp counts of the compactions, double-buffered: one barrier per chunk instead of two
 };
 
 // ------------------------------------------------------------------ producer: condition one frame
@@ -501,12 +501,13 @@ __device__ __forceinline__ uint64_t lm_hash(uint64_t key) {
 __device__ inline int lm_child(const ssd_lm_tables& L, int parent, int w) {
   const uint64_t key = ((uint64_t)(uint32_t)(parent + 1) << 32) | (uint64_t)(uint32_t)w;
   uint64_t s = lm_hash(key) & L.ngram_mask;
-  for (;;) {
+  for (uint64_t tries = 0; tries <= L.ngram_mask; ++tries) {  // bounded: a caller's table without an empty slot must not hang the GPU
     const uint64_t k = L.ngram_keys[s];
     if (k == key) return L.ngram_vals[s];
     if (k == 0ull) return -1;
     s = (s + 1) & L.ngram_mask;
   }
+  return -1;
 }
 // kenlm BaseScore: log10 p(w | ctx) in fp32.  ctx[j] = id of the n-gram made of the last j+1 context words (-1: not
 // in the model).  The longest n-gram ending in w gives the probability; every context longer than the matched one
@@ -554,7 +555,7 @@ __device__ __forceinline__ double lm_partial_score(const ssd_lm_tables& L, int n
 // set of 64-bit keys in global memory (one per CTA): the closed texts that were scored
 __device__ inline void seen_insert(unsigned long long* tab, unsigned long long mask, uint64_t h) {
   unsigned long long s = h & mask;
-  for (;;) {
+  for (unsigned long long tries = 0; tries <= mask; ++tries) {  // the set is sized for twice what an utterance can insert
     const unsigned long long old = atomicCAS(&tab[s], 0ull, (unsigned long long)h);
     if (old == 0ull || old == (unsigned long long)h) return;
     s = (s + 1) & mask;
@@ -562,12 +563,13 @@ __device__ inline void seen_insert(unsigned long long* tab, unsigned long long m
 }
 __device__ inline bool seen_find(unsigned long long* tab, unsigned long long mask, uint64_t h) {
   unsigned long long s = h & mask;
-  for (;;) {
+  for (unsigned long long tries = 0; tries <= mask; ++tries) {
     const unsigned long long k = atomicCAS(&tab[s], 0ull, 0ull);  // an L2 read
     if (k == (unsigned long long)h) return true;
     if (k == 0ull) return false;
     s = (s + 1) & mask;
   }
+  return false;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -1138,18 +1140,18 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
       {
         // ballots over chunks of CONS.  (One scan over per-thread runs of candidates -- two barriers however many
         // candidates -- measured 4 % slower on config 3: the scan's five dependent shuffles cost more than the barriers.)
-        int running = 0;
+        int running = 0, buf = 0;
         SSD_NO_UNROLL
         for (int base_k = 0; base_k < ncand; base_k += CONS) {
           const int k = base_k + tid;
           const bool alive = k < ncand && rscore[k] >= cutoff && rscore[k] != -INFINITY;
           const unsigned m = __ballot_sync(FULL, alive);
-          if (lane == 0) sc->wcnt[warp] = __popc(m);
+          if (lane == 0) sc->wcnt[buf][warp] = __popc(m);
           cons_sync<CONS>();
           int off = running, totc = 0;
 #pragma unroll
           for (int w = 0; w < CONS / 32; ++w) {
-            const int c = sc->wcnt[w];
+            const int c = sc->wcnt[buf][w];
             if (w < warp) off += c;
             totc += c;
           }
@@ -1159,7 +1161,7 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
             if (pos < W) sel[pos] = k;
           }
           running += totc;
-          if (base_k + CONS < ncand) cons_sync<CONS>();  // wcnt is rewritten by the next chunk
+          buf ^= 1;  // the next chunk's counts go to the other buffer: its barrier separates this read from the next write here
         }
         n_alive = running;
       }
@@ -1237,12 +1239,12 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
             const int i = base_i + tid;
             const bool in = i < n_alive && (int)abkt[i] < beta + BK_OFF;
             const unsigned mk = __ballot_sync(FULL, in);
-            if (lane == 0) sc->wcnt[warp] = __popc(mk);
+            if (lane == 0) sc->wcnt[0][warp] = __popc(mk);
             cons_sync<CONS>();
             int off = running, totc = 0;
 #pragma unroll
             for (int w = 0; w < CONS / 32; ++w) {
-              const int cw = sc->wcnt[w];
+              const int cw = sc->wcnt[0][w];
               if (w < warp) off += cw;
               totc += cw;
             }
@@ -1257,8 +1259,8 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
         SSD_NO_UNROLL
         for (int i = tid; i < W; i += CONS) sel[i] = bidx[i];
+        cons_sync<CONS>();  // (at most W alive: sel[] was complete behind phase 4b's barrier)
       }
-      cons_sync<CONS>();
 
       PF_STAMP(6);
       // ---- phase 5: history keys, then keep the best entry per key.
