@@ -122,7 +122,10 @@ int ssd_ctc_beam_grid(const float* log_probs, int64_t B, int64_t T, int64_t V, i
  *                                 + beta, back-off scoring as kenlm's BaseScore, start state <s>
  *   open word                     unk_score_offset if it is not a prefix of any unigram, times len/6 beyond 6 chars
  *   end of utterance              the last word also gets log10 p(</s> | ...), unless its text was already
- *                                 scored as a closed text earlier in the utterance (upstream's score cache)
+ *                                 scored as a closed text earlier in the utterance (upstream's score cache keyed by
+ *                                 text; eos_rescore = 1 selects the other published variant, cache keyed by
+ *                                 (text, is_eos): every final beam is re-scored with the </s> term, a text that ends
+ *                                 closed scoring an empty -- out-of-vocabulary -- last word)
  *   history prune                 key = (last order-1 closed words, open word, last char)
  * The tables are DEVICE arrays built by the caller from the ARPA file (host side: decoding/lm.py):
  *   trie_child  [n_trie_nodes, n_labels] int32: node reached from `node` by beam label k (label 0 = blank is
@@ -147,7 +150,9 @@ typedef struct ssd_lm_tables {
   const float* ngram_backoff;
   uint64_t ngram_mask; /* slots - 1, slots a power of two */
   int32_t n_trie_nodes, n_labels, n_ngrams, order;
-  int32_t bos, eos, unk, reserved;
+  int32_t bos, eos, unk;
+  int32_t eos_rescore; /* 0: a text scored before keeps its score in the final pass (score cache keyed by text);
+                          1: the final pass re-scores every beam with the </s> term (cache keyed by (text, is_eos)) */
   double alpha, beta, unk_score_offset;
 } ssd_lm_tables;
 /* slot hash of the n-gram table: h = key * 0x9E3779B97F4A7C15 (mod 2^64), h ^ (h >> 29).  Exported so that a host

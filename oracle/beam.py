@@ -141,6 +141,13 @@ def _score_no_lm(beams):
     return [(_join(text, nxt), "", part, last, score, score) for text, nxt, part, last, score in beams]
 
 
+# Which key upstream's score cache uses.  "text" (the release this restatement follows, and what the kernel implements): a
+# text that was scored before keeps its score, so the final pass adds no </s> term to it.  "text_eos" (the library's main
+# branch): the final pass re-scores every beam with the </s> term, an already closed text scoring an EMPTY last word.
+# Flip it when the upstream fixtures (make_beam_golden_upstream.py) say so; the per-frame search does not depend on it.
+LM_CACHE_KEY = "text"
+
+
 def _score_lm(beams, lm, cache, pcache, is_eos: bool = False):
     """``_get_lm_beams``: ranking score = acoustic score + LM score of the closed text + partial-word score.
     ``cache`` maps a closed text to (accumulated LM score, end state) and is shared by every frame of an
@@ -149,6 +156,11 @@ def _score_lm(beams, lm, cache, pcache, is_eos: bool = False):
     out = []
     for text, nxt, part, last, score in beams:
         new_text = _join(text, nxt)
+        if LM_CACHE_KEY == "text_eos" and is_eos:
+            prev, state = cache[text]
+            s, _ = lm.score(state, nxt, is_last_word=True)
+            out.append((new_text, "", part, last, score, score + prev + s))  # (no open word in the final pass)
+            continue
         if new_text not in cache:
             prev, state = cache[text]
             s, end_state = lm.score(state, nxt, is_last_word=is_eos)

@@ -52,7 +52,7 @@ class LmTables(C.Structure):
         ("trie_child", C.c_void_p), ("trie_word", C.c_void_p), ("ngram_keys", C.c_void_p), ("ngram_vals", C.c_void_p),
         ("ngram_prob", C.c_void_p), ("ngram_backoff", C.c_void_p), ("ngram_mask", C.c_uint64),
         ("n_trie_nodes", C.c_int32), ("n_labels", C.c_int32), ("n_ngrams", C.c_int32), ("order", C.c_int32),
-        ("bos", C.c_int32), ("eos", C.c_int32), ("unk", C.c_int32), ("reserved", C.c_int32),
+        ("bos", C.c_int32), ("eos", C.c_int32), ("unk", C.c_int32), ("eos_rescore", C.c_int32),
         ("alpha", C.c_double), ("beta", C.c_double), ("unk_score_offset", C.c_double),
     ]
 

@@ -1510,7 +1510,29 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
                 if (plenF[q] > 0) q_open = q; else q_closed = q;
               }
             double lm;
-            if (q_open >= 0) {
+            if (P.lm.eos_rescore) {
+              // the other published variant (score cache keyed by (text, is_eos)): every final beam is re-scored with
+              // the </s> term.  Upstream's final merge leaves the (text, last word) split of the LAST of the merged
+              // beams, i.e. of the group's lowest-ranked entry: the open prefix scores its open word; the closed one an
+              // empty word, which kenlm takes for <unk> and the decoder for out of vocabulary.
+              double eo = INFINITY, ec = INFINITY;
+              if (q_open >= 0) {
+                const double l = lmtF[q_open] + lm_partial_score(P.lm, trieF[q_open], plenF[q_open]);
+                if (A.sb[q_open] != -INFINITY) eo = A.sb[q_open] + l;
+                if (A.snb[q_open] != -INFINITY && A.snb[q_open] + l < eo) eo = A.snb[q_open] + l;
+              }
+              if (q_closed >= 0) {
+                const double l = lmtF[q_closed];
+                if (A.sb[q_closed] != -INFINITY) ec = A.sb[q_closed] + l;
+                if (A.snb[q_closed] != -INFINITY && A.snb[q_closed] + l < ec) ec = A.snb[q_closed] + l;
+              }
+              if (q_open >= 0 && (q_closed < 0 || eo <= ec)) {
+                const int node = trieF[q_open];
+                lm = lmtF[q_open] + lm_word_score(P.lm, P.lm_factor, ctxF + q_open * CX, node >= 0 ? P.lm.trie_word[node] : -1, true, nullptr);
+              } else {
+                lm = lmtF[q_closed] + lm_word_score(P.lm, P.lm_factor, ctxF + q_closed * CX, -1, true, nullptr);
+              }
+            } else if (q_open >= 0) {
               const bool cached = space_lbl >= 0 && seen_find(seen, seen_mask, hmix(A.H[q_open], (uint32_t)space_lbl));
               const int node = trieF[q_open];
               lm = lmtF[q_open] + lm_word_score(P.lm, P.lm_factor, ctxF + q_open * CX, node >= 0 ? P.lm.trie_word[node] : -1, !cached, nullptr);

@@ -88,6 +88,7 @@ class LanguageModelTables:
     alpha: float
     beta: float
     unk_score_offset: float = UNK_SCORE_OFFSET
+    eos_rescore: int = 0  # see ssd_lm_tables.eos_rescore: which of upstream's two score-cache variants the final pass follows
     _dev: Dict[int, tuple] = field(default_factory=dict, repr=False)
 
     @property
@@ -108,7 +109,7 @@ class LanguageModelTables:
         tc, tw, nk, nv, npb, nbo = held
         return _native.LmTables(tc.data_ptr(), tw.data_ptr(), nk.data_ptr(), nv.data_ptr(), npb.data_ptr(), nbo.data_ptr(),
                                 ctypes.c_uint64(len(self.ngram_keys) - 1), int(self.trie_child.shape[0]), self.n_labels,
-                                int(self.ngram_prob.shape[0]), int(self.order), int(self.bos), int(self.eos), int(self.unk), 0,
+                                int(self.ngram_prob.shape[0]), int(self.order), int(self.bos), int(self.eos), int(self.unk), int(self.eos_rescore),
                                 float(self.alpha), float(self.beta), float(self.unk_score_offset))
 
 

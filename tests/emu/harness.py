@@ -126,7 +126,7 @@ def beam_lm(lib, lp: np.ndarray, lengths, blank: int, pad: int, space: int, tabl
     held = [np.ascontiguousarray(a) for a in (tables.trie_child, tables.trie_word, tables.ngram_keys, tables.ngram_vals,
                                               tables.ngram_prob, tables.ngram_backoff)]
     st = LmTables(*[_ptr(a) for a in held], len(tables.ngram_keys) - 1, held[0].shape[0], held[0].shape[1], held[4].shape[0],
-                  tables.order, tables.bos, tables.eos, tables.unk, 0, tables.alpha, tables.beta, tables.unk_score_offset)
+                  tables.order, tables.bos, tables.eos, tables.unk, tables.eos_rescore, tables.alpha, tables.beta, tables.unk_score_offset)
     lib.check(lib.ssd_ctc_beam_lm(_ptr(lp), B, T, V, T * V, V, _ptr(ln), _ptr(od), blank, pad, space, C.cast(arr, C.c_void_p), n,
                                   C.addressof(st), _ptr(tok), _ptr(cnt), _ptr(sc), _ptr(ws), ws.nbytes, None))
     return [([[int(x) for x in tok[i, b, : cnt[i, b]]] for b in range(B)], sc[i]) for i in range(n)]

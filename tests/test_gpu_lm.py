@@ -70,6 +70,27 @@ def test_lm_beam_vs_oracle(arpas, order, width, prune, bias, alpha, beta, boost)
     assert np.abs(score[0].cpu().numpy() - np.asarray([w[2] for w in want])).max() <= SCORE_ATOL
 
 
+@pytest.mark.parametrize("order,width", [(3, 50), (5, 20)])
+def test_lm_beam_other_cache_variant(arpas, order, width):
+    """ssd_lm_tables.eos_rescore = 1 (score cache keyed by (text, is_eos), the library's main branch) against the oracle's
+    LM_CACHE_KEY = "text_eos"."""
+    sents = _sentences(24, seed=order * 7 + width)
+    T = 110
+    lp, _ = lm_cases.spelled_log_probs(sents, T, seed=width + order + 50)
+    ln = synth.ragged_lengths(len(sents), T, 5).tolist()
+    L = olm.LanguageModel(olm.ArpaModel(arpas[order]), alpha=0.6, beta=0.2)
+    ob.LM_CACHE_KEY = "text_eos"
+    try:
+        want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, -10.0, lm=L).decode_with_lm_scores(lp, ln)
+    finally:
+        ob.LM_CACHE_KEY = "text"
+    tab = plm.build_tables(arpas[order], LABEL_TEXT, 0.6, 0.2)
+    tab.eos_rescore = 1
+    tok, cnt, score = ops.beam_lm_ids(torch.from_numpy(lp), torch.tensor(ln), V.blank_id, V.pad_id, SPACE, tab, [(width, -10.0, 0.0, -5.0)])
+    assert ctc._rows_to_strings(tok[0], cnt[0], TEXT, normalise_space=True) == [w[0] for w in want]
+    assert np.abs(score[0].cpu().numpy() - np.asarray([w[2] for w in want])).max() <= SCORE_ATOL
+
+
 def test_build_decoder_with_lm_path(arpas):
     """The reference's call: build_decoder("beam", vocab, lm_path=..., alpha=..., beta=...) (ctc.py:102-121)."""
     sents = _sentences(12, seed=9)

@@ -160,10 +160,15 @@ def _texts(ids):
     return ["".join(ob.UNK_GLYPH if i == V.unk_id else V.tokens[i] for i in s) for s in ids]
 
 
-def _check(lib, path, lp, ln, width, prune, bias, alpha, beta, tol=2e-5):
+def _check(lib, path, lp, ln, width, prune, bias, alpha, beta, tol=2e-5, eos_rescore=0):
     L = olm.LanguageModel(olm.ArpaModel(path), alpha=alpha, beta=beta)
-    want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, blank_bias=bias, lm=L).decode_with_lm_scores(lp, ln)
+    ob.LM_CACHE_KEY = "text_eos" if eos_rescore else "text"
+    try:
+        want = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, width, prune, blank_bias=bias, lm=L).decode_with_lm_scores(lp, ln)
+    finally:
+        ob.LM_CACHE_KEY = "text"
     tab = plm.build_tables(path, LABEL_TEXT, alpha, beta)
+    tab.eos_rescore = eos_rescore
     (ids, score), = harness.beam_lm(lib, lp, ln, V.blank_id, V.pad_id, SPACE, tab, [(width, prune, bias, -5.0)])
     assert _texts(ids) == [w[0] for w in want]
     assert np.abs(score - np.asarray([w[2] for w in want])).max() <= tol
@@ -296,3 +301,34 @@ def test_lm_kernel_schedule_independence(order, arpa3):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
     assert outs[0] == outs[1] and "[[" in outs[0]
+
+
+@pytest.mark.parametrize("order,width,boost,seed", [(3, 20, 3.0, 1), (5, 30, 3.5, 2), (5, 8, 6.0, 3)])
+def test_lm_kernel_other_cache_variant(lib, arpa3, arpa5, order, width, boost, seed):
+    """ssd_lm_tables.eos_rescore = 1 against the oracle's LM_CACHE_KEY = "text_eos": the library main branch's score cache,
+    keyed by (text, is_eos) -- every final beam re-scored with the </s> term, closed texts scoring an empty last word.
+    Which of the two the reference's installation runs is what the upstream fixtures will tell; both are built."""
+    path = arpa3 if order == 3 else arpa5
+    lp, _ = lm_cases.spelled_log_probs(lm_cases.SENTENCES, 84, seed=seed, boost=boost)
+    ln = [84, 80, 84, 71, 84, 60, 84, 84]
+    a = _check(lib, path, lp, ln, width, -10.0, 0.0, 0.6, 0.3, eos_rescore=1)
+    b = _check(lib, path, lp, ln, width, -10.0, 0.0, 0.6, 0.3, eos_rescore=0)
+    assert [x[2] for x in a] != [x[2] for x in b]  # the variants do differ in the final scores
+
+
+def test_other_cache_variant_by_hand(lib, hand):
+    """'a' + blank + {blank, space}: under eos_rescore the final beam "a" always gets the </s> term; which word is scored
+    last depends on the lowest-ranked merged entry ("a" open: p(a|<s>) p(</s>|<s> a); "a " closed: an empty word)."""
+    a, sp = V.tokens.index("a"), V.tokens.index(" ")
+    lp = np.full((2, 3, V.size), -30.0, dtype=np.float32)
+    lp[:, 0, a] = 0.0
+    lp[:, 1, V.blank_id] = 0.0
+    lp[0, 2, V.blank_id] = 0.0
+    lp[1, 2, V.blank_id] = math.log(0.6)
+    lp[1, 2, sp] = math.log(0.4)
+    want = _check(lib, hand, lp, [3, 3], 10, -10.0, 0.0, 0.7, 0.1, eos_rescore=1)
+    assert [w[0] for w in want] == ["a", "a"]
+    k = 0.7 * math.log(10)
+    with_eos = k * (float(f32(-0.4)) + float(f32(f32(-0.6) + f32(-0.25)))) + 0.1
+    assert want[0][2] - want[0][1] == pytest.approx(with_eos, abs=1e-9)
+    assert want[1][2] - want[1][1] != pytest.approx(with_eos, abs=1e-3)  # the closed entry ranks last: empty word + </s>
