@@ -183,3 +183,25 @@ def test_lm_beam_upstream(golden_dir, tmp_path):
         tok, cnt, score = ops.beam_lm_ids(torch.from_numpy(lp), torch.tensor(ln), V.blank_id, V.pad_id, SPACE, tab, [(width, prune, bias, -5.0)])
         assert ctc._rows_to_strings(tok[0], cnt[0], TEXT, normalise_space=True) == list(z[f"{name}.text"]), name
         assert np.abs(score[0].cpu().numpy() - z[f"{name}.lm_score"]).max() <= SCORE_ATOL, name
+
+
+def test_lm_beam_long_utterances(tmp_path):
+    """Config 4's length (T=4000) through the LM kernel: the scored-text set and the back-pointer store are sized by T;
+    two of the utterances are checked against the oracle."""
+    from silent_speech_decoder_b200 import synth as sy
+
+    words = sy.word_list(300, 31)
+    sents = sy.word_corpus(words, 8, 32, lo=60, hi=90)          # ~500 characters each: 8 frames per character
+    lp, ln = sy.spelled(sents, V.token_to_id, 4000, 33, boost=5.0, rival=2.5)
+    ln[1] = 3777
+    arpa = str(tmp_path / "long3.arpa")
+    sy.write_arpa(arpa, sy.word_corpus(words, 3000, 34) + sents[:4], order=3)   # half of the sentences are in the LM's corpus
+    tab = plm.build_tables(arpa, LABEL_TEXT, 0.6, 0.1)
+    tok, cnt, score = ops.beam_lm_ids(lp, ln, V.blank_id, V.pad_id, SPACE, tab, [(50, -10.0, 0.0, -5.0)])
+    got = ctc._rows_to_strings(tok[0], cnt[0], TEXT, normalise_space=True)
+    assert all(len(g) > 100 for g in got) and torch.isfinite(score).all()
+    L = olm.LanguageModel(olm.ArpaModel(arpa), alpha=0.6, beta=0.1)
+    dec = ob.BeamDecoder(V.tokens, V.blank_id, V.pad_id, 50, -10.0, lm=L)
+    for b in (1, 5):
+        want = dec.decode_with_lm_scores(lp[b : b + 1].numpy(), [int(ln[b])])[0]
+        assert got[b] == want[0] and abs(float(score[0, b]) - want[2]) <= 10 * SCORE_ATOL  # fp32 log-softmax noise over 4000 frames

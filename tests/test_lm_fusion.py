@@ -332,3 +332,26 @@ def test_other_cache_variant_by_hand(lib, hand):
     with_eos = k * (float(f32(-0.4)) + float(f32(f32(-0.6) + f32(-0.25)))) + 0.1
     assert want[0][2] - want[0][1] == pytest.approx(with_eos, abs=1e-9)
     assert want[1][2] - want[1][1] != pytest.approx(with_eos, abs=1e-3)  # the closed entry ranks last: empty word + </s>
+
+
+def test_synthetic_lm_workload_generators(tmp_path):
+    """synth.word_list / word_corpus / write_arpa / spelled (the bench's LM workload): the file parses identically in the
+    oracle and in the product's table builder, and the posteriors spell their sentences."""
+    from silent_speech_decoder_b200 import synth
+
+    words = synth.word_list(120, 5)
+    assert len(set(words)) == 120 and all(w.isalpha() for w in words)
+    corpus = synth.word_corpus(words, 400, 6)
+    path = str(tmp_path / "syn4.arpa")
+    synth.write_arpa(path, corpus, order=4)
+    m = olm.ArpaModel(path)
+    order, tables = plm.parse_arpa(path)
+    assert m.order == order == 4 and sum(len(t) for t in tables) == len(m.ngrams)
+    for gram, (p, b) in list(tables[2].items())[:200]:
+        assert m.ngrams[gram] == (np.float32(p), np.float32(b))
+    t = plm.build_tables(path, LABEL_TEXT, 0.6, 0.0)
+    assert len(t.ngram_prob) == len(m.ngrams) and t.unk >= 0 and t.bos >= 0 and t.eos >= 0
+    lp, ln = synth.spelled(corpus[:3], V.token_to_id, 200, 7, boost=12.0, rival=0.0)
+    from oracle import greedy as og
+
+    assert og.greedy_text(lp.numpy(), ln.tolist(), V.tokens, V.blank_id, V.pad_id) == [c[:99] for c in corpus[:3]]
