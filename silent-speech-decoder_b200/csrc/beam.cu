@@ -81,6 +81,9 @@ namespace ssd {
 #else
 #define SSD_NO_UNROLL_FLAT
 #endif
+#ifndef SSD_BEAM_LM_P3U
+#define SSD_BEAM_LM_P3U 1
+#endif
 #ifndef SSD_BEAM_LSE_INLINE
 #define SSD_BEAM_LSE_INLINE 1
 #endif
@@ -536,7 +539,15 @@ __device__ inline float lm_base_score(const ssd_lm_tables& L, const int* ctx, in
   return prob;
 }
 // LanguageModel.score: alpha * (BaseScore [+ unk offset] [+ BaseScore(</s>)]) * ln10 + beta, in fp64 over fp32 terms
-__device__ inline double lm_word_score(const ssd_lm_tables& L, double factor, const int* ctx, int w, bool eos, int* new_ctx) {
+#ifndef SSD_BEAM_LM_WORD_INLINE
+#define SSD_BEAM_LM_WORD_INLINE 1
+#endif
+#if SSD_BEAM_LM_WORD_INLINE
+__device__ inline
+#else
+__device__ __noinline__  // one copy, off the hot path: only space proposals and the end of an utterance score words
+#endif
+double lm_word_score(const ssd_lm_tables& L, double factor, const int* ctx, int w, bool eos, int* new_ctx) {
   int st[LM_CX];
   double lm = (double)lm_base_score(L, ctx, w, st);
   if (w < 0) lm += L.unk_score_offset;
@@ -1057,8 +1068,14 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
         }
       };
       double m_loc = neg_inf();
-      SSD_NO_UNROLL
+      constexpr int P3U = LM ? SSD_BEAM_LM_P3U : 1;
+      (void)P3U;
+#ifdef SSD_EMU
       for (int k = tid; k < ncand; k += CONS) {
+#else
+#pragma unroll(P3U)  // LM: a proposal waits for a trie / n-gram load from L2; unrolling keeps several in flight
+      for (int k = tid; k < ncand; k += CONS) {
+#endif
         double s;
         uint32_t d;
         if (k < np) {
