@@ -595,15 +595,19 @@ __device__ inline bool seen_find(unsigned long long* tab, unsigned long long mas
 constexpr int BM_LM_CONS = SSD_BEAM_LM_CONS;
 constexpr int BM_LM_THREADS = BM_LM_CONS + 32;
 static_assert(BM_LM_CONS % 32 == 0 && BM_LM_CONS <= 128 && BM_CONS <= 128, "per-warp scratch in Scal holds four consumer warps");
-template <bool LM>
+// WCAP: the capacity (widest beam of the launch) as a compile-time constant for the widths the reference uses, 0 = taken
+// from the launch.  With a constant capacity every W-sized table below sits at a constant shared-memory offset; with a
+// run-time one the compiler re-derives those addresses inside the frame loop (15 % of the executed instructions).
+template <bool LM, int WCAP>
 __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM_LM_MINCTAS : SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
   constexpr int CONS = LM ? BM_LM_CONS : BM_CONS;  // consumer threads; one more warp produces
   constexpr int THREADS = CONS + 32;
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
-  const int VL = P.VL, TS = P.TS, NCAND = P.NCAND;
+  const int VL = P.VL, NCAND = P.NCAND;
 
-  const int WC = P.W;  // capacity: every table below is sized for the widest setting of the launch
+  const int WC = WCAP > 0 ? WCAP : P.W;  // capacity: every table below is sized for the widest setting of the launch
+  const int TS = WCAP > 0 ? beam_table_slots(WCAP) : P.TS;
   unsigned char* const gen_base = sp;
   const size_t gen_stride = prefix_gen_bytes(WC);  // a multiple of 16
   const Prefix gen0 = prefix_at(gen_base, WC);
@@ -619,44 +623,13 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
   int* oslot = (int*)carve(sp, 4 * WC);
   unsigned long long* tkeys = (unsigned long long*)carve(sp, 8 * TS);
   int* tvals = (int*)carve(sp, 4 * TS);
-  double* cscore = (double*)carve(sp, 8 * NCAND);  // LM: the RANKING score (acoustic + LM); the acoustic one is recomputed for survivors
-  uint32_t* cdesc = LM ? nullptr : (uint32_t*)carve(sp, 4 * NCAND);
-  using ai_t = typename std::conditional<LM, unsigned short, int>::type;  // candidate / alive indices (LM: capacity < 65536)
-  using bk_t = typename std::conditional<LM, unsigned char, int>::type;   // bucket of an alive entry
-  ai_t* aidx = (ai_t*)carve(sp, sizeof(ai_t) * NCAND);
-  bk_t* abkt = (bk_t*)carve(sp, beam_scratch_bytes(WC, NCAND, LM));  // after the cut this scratch holds the history-key table
-  ai_t* blist = reinterpret_cast<ai_t*>(abkt + NCAND);
-  // bucket codes: no-LM int: bucket b, -1 = in, 256 = out.  LM byte: b + 1 with b <= 253, 0 = in, 255 = out
-  constexpr int BK_OFF = LM ? 1 : 0, BK_TOP = LM ? 253 : 255, BK_IN = LM ? 0 : -1, BK_OUT = LM ? 255 : 256;
-  constexpr int CHUNK = LM ? BM_LM_CHUNK : BM_CHUNK;
   int* hist = (int*)carve(sp, 4 * 256);
   int* bidx = (int*)carve(sp, 4 * (WC + 1));
   int* sel = (int*)carve(sp, 4 * (WC + 1));
   int* sel_keep = (int*)carve(sp, 4 * (WC + 1));
   int* sel_slot = (int*)carve(sp, 4 * (WC + 1));
   uint64_t* sel_hk = (uint64_t*)carve(sp, 8 * (WC + 1));
-  float* const rl_base = (float*)carve(sp, 4 * VL);
-  unsigned char* const cs_base = (unsigned char*)carve(sp, VL);
-  float* const rl_1 = (float*)carve(sp, 4 * VL);
-  unsigned char* const cs_1 = (unsigned char*)carve(sp, VL);
-  const ptrdiff_t rl_stride = rl_1 - rl_base, cs_stride = cs_1 - cs_base;
-  auto frame_rec = [&](int i) {
-    FrameRec f;
-    f.rl = rl_base + (i & 1) * rl_stride;
-    f.cs = cs_base + (i & 1) * cs_stride;
-    return f;
-  };
-  int* lab2voc = (int*)carve(sp, 4 * VL);
-  float* const chunk0 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
-  float* const chunk1 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
-  const ptrdiff_t chunk_stride = chunk1 - chunk0;
-  auto chunk_buf = [&](int c) { return chunk0 + (c & 1) * chunk_stride; };
   Scal* sc = (Scal*)carve(sp, sizeof(Scal));
-  // history-key table over the (by then free) abkt/blist scratch: keys, then the best rank per key
-  const int HKS = beam_hk_slots(WC, NCAND);
-  unsigned long long* hk_keys = reinterpret_cast<unsigned long long*>(abkt);
-  unsigned long long* hk_best = hk_keys + HKS;
-  int* hk_idx = reinterpret_cast<int*>(hk_best + HKS);
   // language-model state of the prefixes (two generations) and the candidates' ranking scores (acoustic + LM)
   const int CX = lm_ctx_slots(P.lm.order);
   double* lmt_base = nullptr;   // accumulated LM score of the closed words
@@ -677,8 +650,40 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
     sp = lp0 + 2 * gb;
     lm_gs8 = (int)(gb / 8);
     lm_gs4 = (int)(gb / 4);
-    cfused = cscore;
   }
+  // ---- from here on the offsets depend on the label count (run-time): candidate arrays, frame records, raw chunks
+  double* cscore = (double*)carve(sp, 8 * NCAND);  // LM: the RANKING score (acoustic + LM); the acoustic one is recomputed for survivors
+  uint32_t* cdesc = LM ? nullptr : (uint32_t*)carve(sp, 4 * NCAND);
+  using ai_t = typename std::conditional<LM, unsigned short, int>::type;  // candidate / alive indices (LM: capacity < 65536)
+  using bk_t = typename std::conditional<LM, unsigned char, int>::type;   // bucket of an alive entry
+  ai_t* aidx = (ai_t*)carve(sp, sizeof(ai_t) * NCAND);
+  bk_t* abkt = (bk_t*)carve(sp, beam_scratch_bytes(WC, NCAND, LM));  // after the cut this scratch holds the history-key table
+  ai_t* blist = reinterpret_cast<ai_t*>(abkt + NCAND);
+  // bucket codes: no-LM int: bucket b, -1 = in, 256 = out.  LM byte: b + 1 with b <= 253, 0 = in, 255 = out
+  constexpr int BK_OFF = LM ? 1 : 0, BK_TOP = LM ? 253 : 255, BK_IN = LM ? 0 : -1, BK_OUT = LM ? 255 : 256;
+  constexpr int CHUNK = LM ? BM_LM_CHUNK : BM_CHUNK;
+  float* const rl_base = (float*)carve(sp, 4 * VL);
+  unsigned char* const cs_base = (unsigned char*)carve(sp, VL);
+  float* const rl_1 = (float*)carve(sp, 4 * VL);
+  unsigned char* const cs_1 = (unsigned char*)carve(sp, VL);
+  const ptrdiff_t rl_stride = rl_1 - rl_base, cs_stride = cs_1 - cs_base;
+  auto frame_rec = [&](int i) {
+    FrameRec f;
+    f.rl = rl_base + (i & 1) * rl_stride;
+    f.cs = cs_base + (i & 1) * cs_stride;
+    return f;
+  };
+  int* lab2voc = (int*)carve(sp, 4 * VL);
+  float* const chunk0 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
+  float* const chunk1 = (float*)carve(sp, (size_t)CHUNK * P.V * 4);
+  const ptrdiff_t chunk_stride = chunk1 - chunk0;
+  auto chunk_buf = [&](int c) { return chunk0 + (c & 1) * chunk_stride; };
+  // history-key table over the (by then free) abkt/blist scratch: keys, then the best rank per key
+  const int HKS = beam_hk_slots(WC, NCAND);
+  unsigned long long* hk_keys = reinterpret_cast<unsigned long long*>(abkt);
+  unsigned long long* hk_best = hk_keys + HKS;
+  int* hk_idx = reinterpret_cast<int*>(hk_best + HKS);
+  if constexpr (LM) cfused = cscore;
   const double* const rscore = cscore;  // what ranks and prunes a candidate
   unsigned long long* const seen = LM ? P.seen + (int64_t)blockIdx.x * P.seen_cap : nullptr;
   (void)CX; (void)lm_gs4;
@@ -1588,16 +1593,35 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
 }
 
 // ------------------------------------------------------------------ host side
-static int beam_grid(int64_t B, size_t smem, bool lm) {
+// The instantiations: capacity as a constant for the reference's widths (config_builder.py:68-93: 20 / 50 / 100), run-time
+// otherwise.  SSD_BEAM_PICK(lm, width, F) evaluates F(kernel) with the instantiation serving that launch.
+#ifndef SSD_BEAM_WCAP
+#define SSD_BEAM_WCAP 1
+#endif
+#if SSD_BEAM_WCAP
+#define SSD_BEAM_PICK(lm, width, F)                                                 \
+  ((lm) ? F((beam_kernel<true, 0>)) /* measured: no gain for the LM kernel (67.5 k against 66.6 k), one instance */ \
+        : ((width) == 50 ? F((beam_kernel<false, 50>))                                \
+           : (width) == 20 ? F((beam_kernel<false, 20>))                              \
+           : (width) == 100 ? F((beam_kernel<false, 100>))                            \
+           : (width) == 1 ? F((beam_kernel<false, 1>))                                \
+           : (width) == 10 ? F((beam_kernel<false, 10>))                              \
+           : (width) == 200 ? F((beam_kernel<false, 200>)) : F((beam_kernel<false, 0>))))
+#else
+#define SSD_BEAM_PICK(lm, width, F) ((lm) ? F((beam_kernel<true, 0>)) : F((beam_kernel<false, 0>)))
+#endif
+
+static int beam_grid(int64_t B, size_t smem, bool lm, int width) {
 #ifdef SSD_EMU
-  (void)smem; (void)lm;
+  (void)smem; (void)lm; (void)width;
   return (int)(B < 3 ? B : 3);
 #else
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (lm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<true>, BM_LM_THREADS, smem);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel<false>, BM_THREADS, smem);
+#define SSD_F_OCC(K) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, lm ? BM_LM_THREADS : BM_THREADS, smem)
+  SSD_BEAM_PICK(lm, width, SSD_F_OCC);
+#undef SSD_F_OCC
   if (per_sm < 1) per_sm = 1;
   const int64_t g = (int64_t)sms * per_sm;
   return (int)(B < g ? B : g);
@@ -1627,7 +1651,7 @@ static int beam_grid_for(int64_t items, int64_t V, int VL, int width, size_t* sm
   const size_t smem = beam_smem_bytes(width, (int)V, VL, TS, NCAND, lm_order);
   if (smem_out) *smem_out = smem;
   if (smem > 227 * 1024) return 0;
-  int grid = beam_grid(items, smem, lm_order > 0);
+  int grid = beam_grid(items, smem, lm_order > 0, width);
   const int gmax = beam_max_grid();
   return grid > gmax ? gmax : grid;
 }
@@ -1695,8 +1719,9 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   const int grid = beam_grid_for(B * n_set, V, P.VL, width, &smem, lm_order);
   if (grid < 1) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
 #ifndef SSD_EMU
-  cudaError_t e = lm ? cudaFuncSetAttribute(beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                     : cudaFuncSetAttribute(beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define SSD_F_ATTR(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+  cudaError_t e = SSD_BEAM_PICK(lm != nullptr, width, SSD_F_ATTR);
+#undef SSD_F_ATTR
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
 #endif
   P.node_cap = beam_node_cap(T, width);
@@ -1715,11 +1740,9 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   e = cudaMemsetAsync(P.counter, 0, 256, stream);
   if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "beam: cudaMemsetAsync: %s", cudaGetErrorString(e));
 #endif
-  if (lm) {
-    SSD_LAUNCH(beam_kernel<true>, (unsigned)grid, BM_LM_THREADS, smem, stream, P);
-  } else {
-    SSD_LAUNCH(beam_kernel<false>, (unsigned)grid, BM_THREADS, smem, stream, P);
-  }
+#define SSD_F_GO(K) (SSD_LAUNCH(K, (unsigned)grid, (lm ? BM_LM_THREADS : BM_THREADS), smem, stream, P), 0)
+  (void)SSD_BEAM_PICK(lm != nullptr, width, SSD_F_GO);
+#undef SSD_F_GO
   return check_launch("beam_kernel");
 }
 
