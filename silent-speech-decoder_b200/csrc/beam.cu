@@ -137,7 +137,7 @@ struct BeamParams {
 // candidate capacity under LM scores: every live prefix proposes every non-blank label (no staircase bound)
 __host__ __device__ inline int beam_ncand_cap_lm(int W, int VL) { return (2 * W + W * (VL - 1) + 31) / 32 * 32; }
 
-__host__ __device__ inline int beam_ncand_cap(int W, int VL) {
+__host__ __device__ constexpr int beam_ncand_cap(int W, int VL) {
   // 2 entries per live prefix + staircase sum_{i<W} min(VL-1, W/(i+1)+1)
   long n = 2L * W;
   for (int i = 0; i < W; ++i) {
@@ -596,15 +596,17 @@ constexpr int BM_LM_CONS = SSD_BEAM_LM_CONS;
 constexpr int BM_LM_THREADS = BM_LM_CONS + 32;
 static_assert(BM_LM_CONS % 32 == 0 && BM_LM_CONS <= 128 && BM_CONS <= 128, "per-warp scratch in Scal holds four consumer warps");
 // WCAP: the capacity (widest beam of the launch) as a compile-time constant for the widths the reference uses, 0 = taken
-// from the launch.  With a constant capacity every W-sized table below sits at a constant shared-memory offset; with a
+// from the launch.  VLC: likewise the label count (47 = the reference's 48-token vocabulary without pad), which fixes the
+// candidate capacity and with it every remaining offset but the raw chunks' (config 3: another +4.7 % / +2.3 %).  With a constant capacity every W-sized table below sits at a constant shared-memory offset; with a
 // run-time one the compiler re-derives those addresses inside the frame loop (15 % of the executed instructions).
-template <bool LM, int WCAP>
+template <bool LM, int WCAP, int VLC = 0>
 __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM_LM_MINCTAS : SSD_BEAM_MINCTAS) beam_kernel(const BeamParams P) {
   constexpr int CONS = LM ? BM_LM_CONS : BM_CONS;  // consumer threads; one more warp produces
   constexpr int THREADS = CONS + 32;
   SSD_DYN_SMEM(smem_raw);
   unsigned char* sp = smem_raw;
-  const int VL = P.VL, NCAND = P.NCAND;
+  constexpr int NCAND_C = (VLC > 0 && WCAP > 0 && !LM) ? beam_ncand_cap(WCAP > 0 ? WCAP : 1, VLC > 0 ? VLC : 2) : 0;
+  const int VL = VLC > 0 ? VLC : P.VL, NCAND = NCAND_C > 0 ? NCAND_C : P.NCAND;
 
   const int WC = WCAP > 0 ? WCAP : P.W;  // capacity: every table below is sized for the widest setting of the launch
   const int TS = WCAP > 0 ? beam_table_slots(WCAP) : P.TS;
@@ -1601,17 +1603,19 @@ __global__ void __launch_bounds__(LM ? BM_LM_THREADS : BM_THREADS, LM ? SSD_BEAM
 #if SSD_BEAM_WCAP
 #define SSD_BEAM_PICK(lm, width, F)                                                 \
   ((lm) ? F((beam_kernel<true, 0>)) /* measured: no gain for the LM kernel (67.5 k against 66.6 k), one instance */ \
-        : ((width) == 50 ? F((beam_kernel<false, 50>))                                \
-           : (width) == 20 ? F((beam_kernel<false, 20>))                              \
-           : (width) == 100 ? F((beam_kernel<false, 100>))                            \
+        : ((width) == 50 ? (vl47 ? F((beam_kernel<false, 50, 47>)) : F((beam_kernel<false, 50>)))  \
+           : (width) == 20 ? (vl47 ? F((beam_kernel<false, 20, 47>)) : F((beam_kernel<false, 20>)))    \
+           : (width) == 100 ? (vl47 ? F((beam_kernel<false, 100, 47>)) : F((beam_kernel<false, 100>))) \
            : (width) == 1 ? F((beam_kernel<false, 1>))                                \
            : (width) == 10 ? F((beam_kernel<false, 10>))                              \
            : (width) == 200 ? F((beam_kernel<false, 200>)) : F((beam_kernel<false, 0>))))
 #else
-#define SSD_BEAM_PICK(lm, width, F) ((lm) ? F((beam_kernel<true, 0>)) : F((beam_kernel<false, 0>)))
+#define SSD_BEAM_PICK(lm, width, F) ((void)vl47, (lm) ? F((beam_kernel<true, 0>)) : F((beam_kernel<false, 0>)))
 #endif
 
-static int beam_grid(int64_t B, size_t smem, bool lm, int width) {
+static int beam_grid(int64_t B, size_t smem, bool lm, int width, int vl) {
+  const bool vl47 = vl == 47;
+  (void)vl47;
 #ifdef SSD_EMU
   (void)smem; (void)lm; (void)width;
   return (int)(B < 3 ? B : 3);
@@ -1651,7 +1655,7 @@ static int beam_grid_for(int64_t items, int64_t V, int VL, int width, size_t* sm
   const size_t smem = beam_smem_bytes(width, (int)V, VL, TS, NCAND, lm_order);
   if (smem_out) *smem_out = smem;
   if (smem > 227 * 1024) return 0;
-  int grid = beam_grid(items, smem, lm_order > 0, width);
+  int grid = beam_grid(items, smem, lm_order > 0, width, VL);
   const int gmax = beam_max_grid();
   return grid > gmax ? gmax : grid;
 }
@@ -1718,6 +1722,8 @@ int beam_launch(const float* lp, int64_t B, int64_t T, int64_t V, int64_t sb, in
   size_t smem = 0;
   const int grid = beam_grid_for(B * n_set, V, P.VL, width, &smem, lm_order);
   if (grid < 1) return fail(SSD_ERR_UNSUPPORTED, "beam: beam_width %d needs %zu bytes of shared memory (> 227 KB)", width, smem);
+  const bool vl47 = P.VL == 47;
+  (void)vl47;
 #ifndef SSD_EMU
 #define SSD_F_ATTR(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
   cudaError_t e = SSD_BEAM_PICK(lm != nullptr, width, SSD_F_ATTR);
